@@ -1,0 +1,178 @@
+/*
+ * nats_b200.h -- C ABI of libnats_b200.so: the B200 (sm_100a) implementation of the hot path of
+ * lukecq1231/nats (scripts/nats.py).
+ *
+ * The reference has no FFI layer: its operator boundary is the set of compiled `theano.function`
+ * callables (f_init, f_next, f_log_probs, f_cost, f_grad_shared, f_update -- nats.py:817, 871, 1320, 1336,
+ * 1160, 1170) plus the `tparams` dict of shared variables (nats.py:72-77).  Each entry point below names the
+ * reference construct it replaces.  A maintainer of the reference binds these with ctypes (see
+ * INTEGRATION.md); nats_b200/nats.py is exactly that binding.
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, a cudaStream_t passed as void*.  No torch / C++ types.
+ *   - Every data pointer is a DEVICE pointer (host code stages inputs; the host-side shim owns the copies).
+ *   - Layouts are the reference's: time-major [T, B, feat], float32, token ids int64 (nats.py:237-240).
+ *   - Parameters / gradients / optimiser state live in ONE flat float32 buffer each, in the packed device
+ *     layout described by nats_param_layout() (gate and candidate matrices of every GRU are stored side by
+ *     side as [rows, 3*dim] so one GEMM serves both; nats.py:283-300 keeps them as separate tensors).
+ *   - Nothing allocates, nothing synchronises the host: the caller passes a workspace sized by the
+ *     *_workspace_bytes() queries, and all work is enqueued on `stream` (CUDA-graph capturable).
+ *   - Return value: 0 = ok, non-zero = error; nats_last_error() returns a message (thread-local).
+ *   - One host thread per context (the reference is single-threaded per process, gen.py:78-85).
+ */
+#ifndef NATS_B200_H
+#define NATS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* all entry points below are exported; everything else in the library has hidden visibility */
+#pragma GCC visibility push(default)
+
+#define NATS_NUM_PARAMS 43          /* nats.py:613-654 */
+#define NATS_GRAD_TAIL 32           /* extra floats after the parameter area of a gradient buffer:
+                                       [0] = sum_b cost_b * scale (so one allreduce carries cost + grads) */
+
+typedef struct nats_ctx nats_ctx_t; /* opaque: device id, SM count, small device scratch */
+
+typedef struct {
+    int32_t n_words;   /* V : options['n_words']  */
+    int32_t dim_word;  /* W : options['dim_word'] */
+    int32_t dim;       /* D : options['dim']      */
+    int32_t dim_att;   /* A : options['dim_att']  */
+} nats_dims_t;
+
+/* One reference-named tensor inside the flat buffer: element (r, c) lives at offset + r*ld + c. */
+typedef struct {
+    char name[32];     /* reference key, e.g. "encoder_U" */
+    int64_t offset;    /* in floats from the start of the flat buffer */
+    int32_t rows, cols, ld;
+    int32_t ndim;      /* 1 or 2: rank of the reference tensor (vectors have rows == 1) */
+} nats_param_view_t;
+
+const char* nats_last_error(void);
+int nats_version(void);
+
+int nats_ctx_create(int device, nats_ctx_t** out);
+int nats_ctx_destroy(nats_ctx_t* ctx);
+
+/* replaces: init_params key order / zipp / unzip / itemlist (nats.py:31-46, 613-654).
+ * Fills views[NATS_NUM_PARAMS] in the reference order; *total_floats = size of a parameter buffer (a multiple
+ * of 32 floats; padding stays zero).  Gradient buffers need total_floats + NATS_GRAD_TAIL floats. */
+int nats_param_layout(const nats_dims_t* dims, nats_param_view_t* views, int64_t* total_floats);
+
+/* ---------------------------------------------------------------- training graph (build_model) ---- */
+/* Workspace for one (Tx, Ty, B) problem: saved activations for the backward + scratch. */
+int64_t nats_train_workspace_bytes(const nats_dims_t* dims, int Tx, int Ty, int B);
+
+/* replaces: f_log_probs (nats.py:1320) = build_model forward (nats.py:658-772).
+ * x [Tx,B] i64, x_mask [Tx,B] f32, y [Ty,B] i64, y_mask [Ty,B] f32  ->  cost [B] f32 (per-sample NLL).
+ * Leaves in `ws` everything nats_train_bwd needs. */
+int nats_train_fwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                   const int64_t* x, const float* x_mask, const int64_t* y, const float* y_mask,
+                   int Tx, int Ty, int B, void* ws, int64_t ws_bytes, float* cost);
+
+/* replaces: tensor.grad(cost.mean(), wrt=itemlist(tparams)) (nats.py:1323, 1340), hand-written reverse mode.
+ * Must follow nats_train_fwd on the same ws / inputs.  Overwrites grads[0 .. total_floats + NATS_GRAD_TAIL):
+ * grads = d( scale * sum_b cost_b ) / d params (scale = 1/B_global), grads[total_floats] = scale*sum_b cost_b. */
+int nats_train_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                   const int64_t* x, const float* x_mask, const int64_t* y, const float* y_mask,
+                   int Tx, int Ty, int B, void* ws, int64_t ws_bytes, float scale, float* grads);
+
+/* Finer-grained pieces of the same graph; all operate on the same workspace. */
+int nats_encoder_fwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                     const int64_t* x, const float* x_mask /* NULL = all ones */, int Tx, int Ty, int B,
+                     void* ws, int64_t ws_bytes);                       /* nats.py:700-724 */
+int nats_decoder_scan_fwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                          const int64_t* y, const float* x_mask, const float* y_mask, int Tx, int Ty, int B,
+                          void* ws, int64_t ws_bytes);                  /* nats.py:730-742 */
+int nats_readout_nll_fwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                         const int64_t* y, const float* y_mask, int Tx, int Ty, int B,
+                         void* ws, int64_t ws_bytes, float* cost);      /* nats.py:753-770 */
+int nats_readout_nll_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                         const int64_t* y, const float* y_mask, int Tx, int Ty, int B,
+                         void* ws, int64_t ws_bytes, float scale, float* grads);
+int nats_decoder_scan_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                          const int64_t* y, const float* x_mask, const float* y_mask, int Tx, int Ty, int B,
+                          void* ws, int64_t ws_bytes, float* grads);
+int nats_encoder_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                     const int64_t* x, const float* x_mask, const int64_t* y, int Tx, int Ty, int B,
+                     void* ws, int64_t ws_bytes, float* grads);
+
+/* Read-only views into a training workspace (for tests / alignment dumps): name in
+ * {"ctx","init_state","dec_h","dec_ctx","dec_alpha","pctx","logits"}; returns device pointer or NULL. */
+const float* nats_train_ws_view(const nats_dims_t* dims, int Tx, int Ty, int B, void* ws, const char* name);
+
+/* ---------------------------------------------------------------- sampler graph (build_sampler) ---- */
+int64_t nats_sampler_workspace_bytes(const nats_dims_t* dims, int Tx, int n);
+
+/* replaces: f_init (nats.py:789-817).  x [Tx,n] i64 -> init_state [n,D], ctx [Tx,n,C]; additionally returns
+ * pctx [Tx,n,A] = ctx.Wc_att + b_att (nats.py:493-494) so that f_next need not recompute it every step. */
+int nats_sampler_init(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                      const int64_t* x, int Tx, int n, void* ws, int64_t ws_bytes,
+                      float* init_state, float* ctx_out, float* pctx_out);
+
+/* replaces: f_next (nats.py:821-871) = embed (y<0 -> zeros) + one _step_slice (nats.py:498-572, mask == 1,
+ * no context mask) + readout softmax (nats.py:850-861) + multinomial sample (nats.py:864).
+ * ctx element (t, i, c) is read at ctx_in[t*ctx_tstride + i*ctx_bstride + c] (bstride 0 = all n hypotheses
+ * share one source, i.e. numpy.tile(ctx0,[live_k,1]) of nats.py:958 without the copy).  pctx likewise
+ * (pctx_in may be NULL: then it is recomputed from ctx as the reference does).
+ * Outputs in the reference order (nats.py:870): probs [n,V], sample [n] i64, state' [n,D], alphaT [n,Tx],
+ * ctxs [n,C], acc_ctx' [n,C], acc_alpha' [n,Tx]. */
+int nats_sampler_next(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                      const int64_t* y, const float* ctx_in, int64_t ctx_tstride, int64_t ctx_bstride,
+                      const float* pctx_in, int64_t pctx_tstride, int64_t pctx_bstride,
+                      const float* state, const float* acc_ctx, const float* acc_alpha, int Tx, int n,
+                      uint64_t rng_seed, uint64_t rng_step, void* ws, int64_t ws_bytes,
+                      float* probs, int64_t* sample, float* state_out, float* alphaT, float* ctxs,
+                      float* acc_ctx_out, float* acc_alpha_out);
+
+/* ---------------------------------------------------------------- gradient clip + optimisers ------ */
+/* replaces: L2 term (nats.py:1326-1332) and global-norm clip (nats.py:1344-1353) on the flat buffer:
+ * grads += 2*decay_c*params (if decay_c>0); g2 = sum grads^2; if clip_c>0 and g2>clip_c^2: grads *= clip_c/sqrt(g2).
+ * stats[0] = g2 (pre-clip), stats[1] = sum params^2 (only if decay_c>0).  n = total_floats. */
+int nats_grad_clip(nats_ctx_t* ctx, void* stream, int64_t n, const float* params, float* grads,
+                   float decay_c, float clip_c, float* stats /* device, >= 4 floats */);
+
+/* replaces: adadelta (nats.py:1145-1173). grad_shared: rg2 <- rho rg2 + (1-rho) g^2 (zg IS the grads buffer);
+ * update: ud = -sqrt(ru2+eps)/sqrt(rg2+eps)*zg; ru2 <- rho ru2 + (1-rho) ud^2; p <- p + ud. */
+int nats_adadelta_grad_shared(nats_ctx_t* ctx, void* stream, int64_t n, const float* zg, float* rg2, float rho);
+int nats_adadelta_update(nats_ctx_t* ctx, void* stream, int64_t n, float* params, const float* zg,
+                         float* ru2, const float* rg2, float rho, float eps);
+/* replaces: adam (nats.py:1106-1142); step = value of i before the update (0-based). */
+int nats_adam_update(nats_ctx_t* ctx, void* stream, int64_t n, float* params, const float* g,
+                     float* m, float* v, int64_t step);
+/* replaces: rmsprop (nats.py:1176-1206). */
+int nats_rmsprop_grad_shared(nats_ctx_t* ctx, void* stream, int64_t n, const float* zg, float* rg, float* rg2);
+int nats_rmsprop_update(nats_ctx_t* ctx, void* stream, int64_t n, float* params, const float* zg,
+                        float* ud, const float* rg, const float* rg2);
+
+/* ---------------------------------------------------------------- beam-search distraction --------- */
+/* replaces: the SciPy loop of gen_sample (nats.py:982-995).  Histories are [k_cap, len_cap, dim] arrays of
+ * which rows [0, live_k) x [0, hist_len) are valid.  out [3, live_k]:
+ *   out[0,i] = -kl_factor   * min_s KL(alpha_hist[i,s] || alpha_cur[i])   (scipy.stats.entropy semantics)
+ *   out[1,i] =  ctx_factor  * max_s (1 - cos(ctx_hist[i,s],   ctx_cur[i]))
+ *   out[2,i] =  state_factor* max_s (1 - cos(state_hist[i,s], state_cur[i]))
+ * scratch: >= 3*live_k*hist_len floats. */
+int nats_beam_distraction_scores(nats_ctx_t* ctx, void* stream,
+                                 const float* hist_alpha, const float* hist_ctx, const float* hist_state,
+                                 int len_cap, int hist_len, int live_k, int Tx, int C, int D,
+                                 const float* cur_alpha, const float* cur_ctx, const float* cur_state,
+                                 float kl_factor, float ctx_factor, float state_factor,
+                                 float* scratch, float* out);
+
+/* replaces: the history copies of nats.py:1015-1023: for every new hypothesis j (parent[j] = trans index)
+ * dst[j, 0:hist_len] = src[parent[j], 0:hist_len]; dst[j, hist_len] = cur[parent[j]].  dim = row width. */
+int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, float* dst, const float* cur,
+                             const int32_t* parent, int n_new, int len_cap, int hist_len, int dim);
+
+#pragma GCC visibility pop
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NATS_B200_H */

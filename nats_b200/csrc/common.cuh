@@ -1,0 +1,113 @@
+// common.cuh -- shared helpers for libnats_b200 (sm_100a).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/nats_b200.h"
+
+namespace nats {
+
+// ------------------------------------------------------------------ error handling
+void set_error(const char* fmt, ...);
+
+#define NATS_CUDA_OK(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            nats::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 1;                                                                        \
+        }                                                                                    \
+    } while (0)
+
+#define NATS_LAUNCH_OK()                                                                     \
+    do {                                                                                     \
+        cudaError_t _e = cudaPeekAtLastError();                                              \
+        if (_e != cudaSuccess) {                                                             \
+            nats::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return 1;                                                                        \
+        }                                                                                    \
+    } while (0)
+
+#define NATS_TRY(expr)                \
+    do {                              \
+        int _r = (expr);              \
+        if (_r != 0) return _r;       \
+    } while (0)
+
+#define NATS_REQUIRE(cond, msg)                                                \
+    do {                                                                       \
+        if (!(cond)) {                                                         \
+            nats::set_error("%s:%d: requirement failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \
+            return 2;                                                          \
+        }                                                                      \
+    } while (0)
+
+}  // namespace nats
+
+struct nats_ctx {
+    int device;
+    int num_sms;
+    int max_smem_optin;
+    float* dev_scratch;          // small stream-ordered reduction scratch (kCtxScratchFloats)
+};
+constexpr int kCtxScratchFloats = 16384;
+
+namespace nats {
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up64(int64_t a, int64_t b) { return cdiv64(a, b) * b; }
+
+// ------------------------------------------------------------------ device math
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide reductions (blockDim.x multiple of 32, <= 1024).  `red` = 32 floats of shared memory.
+// All threads receive the result.  Contains __syncthreads(): call from uniform control flow.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.0f;
+    return warp_sum(r);
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : -INFINITY;
+    return warp_max(r);
+}
+
+// streaming (read-once) 128-bit load that does not pollute L1
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+}  // namespace nats

@@ -1,0 +1,394 @@
+// ops_att.cu -- Bahdanau attention with distraction (nats.py:527-546, 569-570): forward and backward.
+//
+// Forward, per decoder step:
+//   att_scores_kernel   e[b,t]  = U_att . tanh(pctx[t,b,:] + ps[b,:] + acc_alpha[b,t]*D_wei) + c_att
+//   att_context_kernel  alpha   = masked softmax_t(e);  c_raw = sum_t alpha[t] cc[t,b,:]   <-- the HBM-bound stream
+//                       ctx     = tanh(U_con*c_raw + W_con*acc_ctx);  acc_ctx += m*ctx;  acc_alpha += m*alpha
+//   The [Tx, C] slab of encoder states of one sample is streamed through shared memory by the TMA engine
+//   (cp.async.bulk + mbarrier ring, one elected warp issues, all warps consume); the grid is
+//   (column slices) x (samples) so that >= 2 CTAs per SM keep ~50 KB of bulk copies in flight each.
+// Backward, per decoder step: att_bwd_ctx_kernel, att_bwd_dalpha_kernel (re-streams cc), att_bwd_softmax_kernel.
+#include "ops.cuh"
+
+namespace nats {
+
+namespace {
+
+constexpr int kAttThreads = 256;
+constexpr int kRowsPerCta = 32;   // scores / dalpha kernels: rows of Tx per CTA
+constexpr int kStages = 4;        // context kernel: bulk-copy ring depth
+constexpr int kStageRows = 16;    // rows of cc per stage
+constexpr int kMaxSlice = 256;    // columns per CTA (one per thread)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// ------------------------------------------------------------------ forward: energies
+__global__ void __launch_bounds__(kAttThreads) att_scores_kernel(const __grid_constant__ AttFwd a) {
+    extern __shared__ float sm[];
+    float* s_ps = sm;
+    float* s_dw = sm + a.A;
+    float* s_ua = sm + 2 * a.A;
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < a.A; i += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < a.ps_nsplit; ++k) s += a.ps_part[k * a.ps_stride + (long long)b * a.A + i];
+        s_ps[i] = s;
+        if (blockIdx.x == 0 && a.ps_save) a.ps_save[(long long)b * a.A + i] = s;
+        s_dw[i] = __ldg(a.D_wei + i);
+        s_ua[i] = __ldg(a.U_att + i);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float catt = __ldg(a.c_att);
+    const int t_end = min(a.Tx, (int)(blockIdx.x + 1) * kRowsPerCta);
+    for (int t = blockIdx.x * kRowsPerCta + warp; t < t_end; t += kAttThreads / 32) {
+        const float accv = a.acc_alpha_in[(long long)b * a.Tx + t];
+        const float* pr = a.pctx + (long long)t * a.pctx_tstride + (long long)b * a.pctx_bstride;
+        float s = 0.f;
+        for (int i = lane; i < a.A; i += 32) s += s_ua[i] * tanhf(__ldg(pr + i) + s_ps[i] + accv * s_dw[i]);
+        s = warp_sum(s);
+        if (lane == 0) a.escore[(long long)b * a.Tx + t] = s + catt;
+    }
+}
+
+// ------------------------------------------------------------------ forward: softmax + context + distraction
+template <bool BULK>
+__global__ void __launch_bounds__(kAttThreads) att_context_kernel(const __grid_constant__ AttFwd a, int slice_len,
+                                                                 int slice_pad) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ float red[32];
+    const int Txp = (a.Tx + 31) & ~31;
+    float* s_alpha = reinterpret_cast<float*>(smem_raw);
+    float* s_tile = s_alpha + Txp;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tile + (BULK ? kStages * kStageRows * slice_pad : 0));
+
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int c0 = blockIdx.x * slice_len;
+    const int len = min(slice_len, a.C - c0);
+    const float* ccb = a.cc + (long long)b * a.cc_bstride + c0;
+    const int nblk = (a.Tx + kStageRows - 1) / kStageRows;
+
+    auto issue = [&](int blk) {   // executed by warp 0
+        const int stage = blk % kStages;
+        const int t0 = blk * kStageRows;
+        const int rows = min(kStageRows, a.Tx - t0);
+        const int lane = tid & 31;
+        if (lane == 0) mbar_arrive_expect_tx(&bars[stage], (uint32_t)(rows * len * 4));
+        __syncwarp();
+        if (lane < rows)
+            bulk_g2s(s_tile + ((long long)stage * kStageRows + lane) * slice_pad,
+                     ccb + (long long)(t0 + lane) * a.cc_tstride, (uint32_t)(len * 4), &bars[stage]);
+    };
+
+    if (BULK) {
+        if (tid == 0) {
+            for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (tid < 32)
+            for (int blk = 0; blk < kStages && blk < nblk; ++blk) issue(blk);
+    }
+
+    // masked softmax over the source positions (nats.py:537-540); max taken over valid positions only
+    float lmax = -INFINITY;
+    for (int t = tid; t < a.Tx; t += kAttThreads) {
+        const float e = a.escore[(long long)b * a.Tx + t];
+        s_alpha[t] = e;
+        const float mk = a.xmask ? a.xmask[(long long)t * a.n + b] : 1.f;
+        if (mk > 0.f) lmax = fmaxf(lmax, e);
+    }
+    float mx = block_max(lmax, red);
+    if (mx == -INFINITY) mx = 0.f;
+    float lsum = 0.f;
+    for (int t = tid; t < a.Tx; t += kAttThreads) {
+        const float mk = a.xmask ? a.xmask[(long long)t * a.n + b] : 1.f;
+        const float w = expf(s_alpha[t] - mx) * mk;
+        s_alpha[t] = w;
+        lsum += w;
+    }
+    const float S = block_sum(lsum, red);
+    const float inv = 1.f / S;
+    __syncthreads();
+
+    // c_raw[c] = sum_t alpha[t] * cc[t, b, c]   (nats.py:541)
+    float acc = 0.f;
+    if (BULK) {
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int stage = blk % kStages;
+            mbar_wait(&bars[stage], (uint32_t)((blk / kStages) & 1));
+            const int t0 = blk * kStageRows;
+            const int rows = min(kStageRows, a.Tx - t0);
+            if (tid < len) {
+                const float* tp = s_tile + (long long)stage * kStageRows * slice_pad + tid;
+#pragma unroll 4
+                for (int r = 0; r < rows; ++r) acc = fmaf(s_alpha[t0 + r], tp[r * slice_pad], acc);
+            }
+            __syncthreads();   // every thread is done with this stage before it is refilled
+            if (tid < 32 && blk + kStages < nblk) issue(blk + kStages);
+        }
+    } else {
+        if (tid < len) {
+            const float* p = ccb + tid;
+            int t = 0;
+            for (; t + 8 <= a.Tx; t += 8) {
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (long long)(t + k) * a.cc_tstride);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = fmaf(s_alpha[t + k], v[k], acc);
+            }
+            for (; t < a.Tx; ++t) acc = fmaf(s_alpha[t], __ldg(p + (long long)t * a.cc_tstride), acc);
+        }
+    }
+
+    const float m = a.ymask ? a.ymask[b] : 1.f;
+    if (tid < len) {
+        const int gc = c0 + tid;
+        const long long o = (long long)b * a.C + gc;
+        const float craw = acc * inv;
+        const float accc = a.acc_ctx_in[o];
+        const float cv = tanhf(__ldg(a.U_con + gc) * craw + __ldg(a.W_con + gc) * accc);   // nats.py:545-546
+        if (a.craw_out) a.craw_out[o] = craw;
+        a.ctx_out[o] = cv;
+        a.acc_ctx_out[o] = accc + m * cv;                                                   // nats.py:569
+    }
+    if (blockIdx.x == 0) {
+        for (int t = tid; t < a.Tx; t += kAttThreads) {
+            const long long o = (long long)b * a.Tx + t;
+            const float al = s_alpha[t] * inv;
+            a.alpha_out[o] = al;
+            a.acc_alpha_out[o] = a.acc_alpha_in[o] + m * al;                                // nats.py:570
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backward kernels
+__global__ void att_bwd_ctx_kernel(const __grid_constant__ AttBwd a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * a.C) return;
+    const int b = idx / a.C, c = idx - b * a.C;
+    const float m = a.ymask ? a.ymask[b] : 1.f;
+    float d = a.dctx_a ? a.dctx_a[idx] : 0.f;
+    for (int s = 0; s < a.dctx_nsplit; ++s) d += a.dctx_part[s * a.dctx_stride + idx];
+    const float dacc = a.dacc_ctx_in[idx];
+    d += m * dacc;
+    const float cv = a.ctx[idx];
+    const float dq = d * (1.f - cv * cv);
+    a.dq[idx] = dq;
+    a.dcraw[idx] = dq * __ldg(a.U_con + c);
+    a.dacc_ctx_out[idx] = dacc + dq * __ldg(a.W_con + c);
+}
+
+__global__ void __launch_bounds__(kAttThreads) att_bwd_dalpha_kernel(const __grid_constant__ AttBwd a) {
+    extern __shared__ __align__(16) float s_dcraw[];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < a.C; i += blockDim.x) s_dcraw[i] = a.dcraw[(long long)b * a.C + i];
+    __syncthreads();
+    const float m = a.ymask ? a.ymask[b] : 1.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = ((a.C & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.cc) & 15) == 0);
+    const int t_end = min(a.Tx, (int)(blockIdx.x + 1) * kRowsPerCta);
+    for (int t = blockIdx.x * kRowsPerCta + warp; t < t_end; t += kAttThreads / 32) {
+        const float* row = a.cc + ((long long)t * a.B + b) * a.C;
+        float s = 0.f;
+        if (vec) {
+            const int n4 = a.C >> 2;
+            const float4* d4 = reinterpret_cast<const float4*>(s_dcraw);
+#pragma unroll 4
+            for (int i = lane; i < n4; i += 32) {
+                const float4 v = ldg_stream4(row + 4 * i);
+                const float4 d = d4[i];
+                s = fmaf(v.x, d.x, s); s = fmaf(v.y, d.y, s); s = fmaf(v.z, d.z, s); s = fmaf(v.w, d.w, s);
+            }
+        } else {
+            for (int i = lane; i < a.C; i += 32) s = fmaf(__ldg(row + i), s_dcraw[i], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            const long long o = (long long)b * a.Tx + t;
+            a.dalpha[o] = s + m * a.dacc_alpha[o];
+        }
+    }
+}
+
+constexpr int kSoftThreads = 512;
+constexpr int kSoftWarps = kSoftThreads / 32;
+constexpr int kMaxAk = 8;   // A <= 256
+
+__global__ void __launch_bounds__(kSoftThreads) att_bwd_softmax_kernel(const __grid_constant__ AttBwd a) {
+    extern __shared__ float sm[];
+    __shared__ float red[32];
+    const int A = a.A, Tx = a.Tx, b = blockIdx.x, tid = threadIdx.x;
+    float* s_de = sm;                 // [Tx]
+    float* s_acc = s_de + Tx;         // [Tx]
+    float* s_ps = s_acc + Tx;         // [A]
+    float* s_dw = s_ps + A;           // [A]
+    float* s_ua = s_dw + A;           // [A]
+    float* s_part = s_ua + A;         // [warps][3][A]
+
+    float ldot = 0.f;
+    for (int t = tid; t < Tx; t += kSoftThreads) {
+        const long long o = (long long)b * Tx + t;
+        ldot += a.alpha[o] * a.dalpha[o];
+    }
+    const float dot = block_sum(ldot, red);
+    float lgc = 0.f;
+    for (int t = tid; t < Tx; t += kSoftThreads) {
+        const long long o = (long long)b * Tx + t;
+        const float de = a.alpha[o] * (a.dalpha[o] - dot);      // masked-softmax backward (nats.py:537-540)
+        s_de[t] = de;
+        s_acc[t] = a.acc_alpha[o];
+        lgc += de;
+    }
+    for (int i = tid; i < A; i += kSoftThreads) {
+        s_ps[i] = a.ps[(long long)b * A + i];
+        s_dw[i] = __ldg(a.D_wei + i);
+        s_ua[i] = __ldg(a.U_att + i);
+    }
+    const float gc = block_sum(lgc, red);
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    float r_dps[kMaxAk], r_gu[kMaxAk], r_gd[kMaxAk];
+#pragma unroll
+    for (int k = 0; k < kMaxAk; ++k) { r_dps[k] = 0.f; r_gu[k] = 0.f; r_gd[k] = 0.f; }
+    for (int t = warp; t < Tx; t += kSoftWarps) {
+        const float de = s_de[t], accv = s_acc[t];
+        const long long base = ((long long)t * a.B + b) * A;
+        float rowsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxAk; ++k) {
+            const int i = lane + 32 * k;
+            if (i < A) {
+                const float z = tanhf(a.pctx[base + i] + s_ps[i] + accv * s_dw[i]);
+                const float dzp = de * s_ua[i] * (1.f - z * z);
+                a.dpctx[base + i] += dzp;
+                r_dps[k] += dzp;
+                r_gu[k] += de * z;
+                r_gd[k] += accv * dzp;
+                rowsum += dzp * s_dw[i];
+            }
+        }
+        rowsum = warp_sum(rowsum);
+        if (lane == 0) a.dacc_alpha[(long long)b * Tx + t] += rowsum;           // through nats.py:532
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxAk; ++k) {
+        const int i = lane + 32 * k;
+        if (i < A) {
+            s_part[(warp * 3 + 0) * A + i] = r_dps[k];
+            s_part[(warp * 3 + 1) * A + i] = r_gu[k];
+            s_part[(warp * 3 + 2) * A + i] = r_gd[k];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < A; i += kSoftThreads) {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        for (int w = 0; w < kSoftWarps; ++w) {
+            d0 += s_part[(w * 3 + 0) * A + i];
+            d1 += s_part[(w * 3 + 1) * A + i];
+            d2 += s_part[(w * 3 + 2) * A + i];
+        }
+        a.dps[(long long)b * A + i] = d0;
+        a.gatt_part[(long long)b * (2 * A + 1) + i] += d1;
+        a.gatt_part[(long long)b * (2 * A + 1) + A + i] += d2;
+    }
+    if (tid == 0) a.gatt_part[(long long)b * (2 * A + 1) + 2 * A] += gc;
+}
+
+inline size_t context_smem(int Tx, bool bulk, int slice_pad) {
+    size_t s = (size_t)((Tx + 31) & ~31) * 4;
+    if (bulk) s += (size_t)kStages * kStageRows * slice_pad * 4 + kStages * 8;
+    return s + 16;
+}
+
+}  // namespace
+
+int attention_setup(const nats_ctx* ctx) {
+    const int lim = ctx->max_smem_optin;
+    NATS_CUDA_OK(cudaFuncSetAttribute(att_context_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NATS_CUDA_OK(cudaFuncSetAttribute(att_context_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NATS_CUDA_OK(cudaFuncSetAttribute(att_bwd_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NATS_CUDA_OK(cudaFuncSetAttribute(att_bwd_dalpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    return 0;
+}
+
+int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
+    NATS_REQUIRE(a.Tx >= 1 && a.n >= 1, "attention shape");
+    {
+        dim3 grid(cdiv(a.Tx, kRowsPerCta), a.n);
+        att_scores_kernel<<<grid, kAttThreads, 3 * a.A * sizeof(float), st>>>(a);
+        NATS_LAUNCH_OK();
+    }
+    // column slices: aim at >= 2 CTAs per SM
+    int target = cdiv(2 * ctx->num_sms, a.n);
+    if (target < 1) target = 1;
+    int slice = cdiv(a.C, target);
+    slice = ((slice + 3) / 4) * 4;
+    if (slice < 32) slice = 32;
+    if (slice > kMaxSlice) slice = kMaxSlice;
+    const int nslices = cdiv(a.C, slice);
+    const int slice_pad = slice;   // multiple of 4 floats -> 16-byte aligned rows in shared memory
+    const bool aligned = ((a.C & 3) == 0) && ((a.cc_tstride & 3) == 0) && ((a.cc_bstride & 3) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.cc) & 15) == 0);
+    bool bulk = aligned;
+    size_t smem = context_smem(a.Tx, bulk, slice_pad);
+    if (bulk && smem > (size_t)ctx->max_smem_optin) { bulk = false; smem = context_smem(a.Tx, false, slice_pad); }
+    NATS_REQUIRE(smem <= (size_t)ctx->max_smem_optin, "source too long for the attention kernel's shared memory");
+    dim3 grid(nslices, a.n);
+    if (bulk) att_context_kernel<true><<<grid, kAttThreads, smem, st>>>(a, slice, slice_pad);
+    else att_context_kernel<false><<<grid, kAttThreads, smem, st>>>(a, slice, slice_pad);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+
+int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a) {
+    NATS_REQUIRE(a.A <= 32 * kMaxAk, "dim_att > 256 not supported by the attention backward kernel");
+    att_bwd_ctx_kernel<<<cdiv(a.B * a.C, 256), 256, 0, st>>>(a);
+    NATS_LAUNCH_OK();
+    {
+        dim3 grid(cdiv(a.Tx, kRowsPerCta), a.B);
+        att_bwd_dalpha_kernel<<<grid, kAttThreads, (size_t)a.C * sizeof(float), st>>>(a);
+        NATS_LAUNCH_OK();
+    }
+    {
+        const size_t smem = ((size_t)2 * a.Tx + 3 * a.A + (size_t)kSoftWarps * 3 * a.A) * sizeof(float);
+        NATS_REQUIRE(smem <= (size_t)ctx->max_smem_optin, "source too long for the attention backward kernel");
+        att_bwd_softmax_kernel<<<a.B, kSoftThreads, smem, st>>>(a);
+        NATS_LAUNCH_OK();
+    }
+    return 0;
+}
+
+}  // namespace nats

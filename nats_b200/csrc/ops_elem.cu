@@ -1,0 +1,299 @@
+// ops_elem.cu -- embedding gather/scatter, GRU gate epilogues (forward + backward), small reductions.
+#include "ops.cuh"
+
+namespace nats {
+
+namespace {
+
+// ------------------------------------------------------------------ embedding
+__global__ void gather_rows_kernel(const float* __restrict__ Wemb, const int64_t* __restrict__ ids, int n_rows, int W,
+                                   int V, int shift, float* __restrict__ out) {
+    const long long total = (long long)n_rows * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / W), w = (int)(i % W);
+        float v = 0.f;
+        if (row >= shift) {
+            const long long id = ids[row - shift];
+            if (id >= 0 && id < V) v = __ldg(Wemb + id * W + w);
+        }
+        out[i] = v;
+    }
+}
+
+__global__ void scatter_add_rows_kernel(float* __restrict__ dWemb, const int64_t* __restrict__ ids, int n_rows, int W,
+                                        int V, int shift, const float* __restrict__ src) {
+    const long long total = (long long)n_rows * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / W), w = (int)(i % W);
+        if (row < shift) continue;
+        const long long id = ids[row - shift];
+        if (id >= 0 && id < V) atomicAdd(dWemb + id * W + w, src[i]);
+    }
+}
+
+// ------------------------------------------------------------------ GRU gates
+struct GateFwdPack { GateFwd g[2]; };
+struct GateBwdPack { GateBwd g[2]; };
+
+template <int MODE>
+__global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, int B, int D) {
+    const GateFwd& a = pack.g[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * D) return;
+    const int b = idx / D, j = idx - b * D;
+    const long long row3 = (long long)b * 3 * D;
+    float gr = 0.f, gu = 0.f, pp = 0.f;
+    for (int s = 0; s < a.nsplit; ++s) {
+        const float* ps = a.part + s * a.part_stride + row3;
+        gr += ps[j]; gu += ps[D + j]; pp += ps[2 * D + j];
+    }
+    float xc;
+    if (MODE == 0) {
+        const float* x = a.xproj + row3;
+        gr += x[j]; gu += x[D + j]; xc = x[2 * D + j];
+    } else {
+        float qr = 0.f, qu = 0.f, qc = 0.f;
+        for (int s = 0; s < a.nsplit2; ++s) {
+            const float* q = a.part2 + s * a.part2_stride + row3;
+            qr += q[j]; qu += q[D + j]; qc += q[2 * D + j];
+        }
+        gr += __ldg(a.bias + j) + qr;
+        gu += __ldg(a.bias + D + j) + qu;
+        pp += __ldg(a.bias + 2 * D + j);
+        xc = qc;
+    }
+    const float r = sigmoidf_(gr), u = sigmoidf_(gu);
+    const float c = tanhf(pp * r + xc);
+    const float hp = a.h_prev ? a.h_prev[(long long)b * a.ld_hprev + j] : 0.f;
+    const float hn = u * hp + (1.f - u) * c;
+    const float m = a.mask ? a.mask[b] : 1.f;
+    const float h = m * hn + (1.f - m) * hp;
+    a.h_out[(long long)b * a.ld_hout + j] = h;
+    if (a.r) {
+        a.r[idx] = r; a.u[idx] = u; a.c[idx] = c; a.p[idx] = pp;
+    }
+    if (a.ctxsum) a.ctxsum[(long long)b * a.ld_ctxsum + j] += m * h;
+}
+
+__global__ void gru_gates_bwd_kernel(const __grid_constant__ GateBwdPack pack, int B, int D) {
+    const GateBwd& a = pack.g[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * D) return;
+    const int b = idx / D, j = idx - b * D;
+    const float m = a.mask ? a.mask[b] : 1.f;
+    float dh = 0.f;
+    if (a.dh_a) dh += a.dh_a[(long long)b * a.ld_a + j];
+    if (a.dh_b) dh += a.dh_b[(long long)b * a.ld_b + j];
+    for (int s = 0; s < a.nsplit; ++s) dh += a.part[s * a.part_stride + (long long)b * a.part_ld + j];
+    for (int s = 0; s < a.nsplit2; ++s) dh += a.part2[s * a.part2_stride + (long long)b * a.part2_ld + j];
+    if (a.mean_grad) dh += m * a.coef[b] * a.mean_grad[(long long)b * a.ld_mean + j];
+    const float r = a.r[idx], u = a.u[idx], c = a.c[idx], p = a.p[idx];
+    const float hp = a.h_prev ? a.h_prev[(long long)b * a.ld_hprev + j] : 0.f;
+    const float dhn = m * dh;
+    const float du = dhn * (hp - c);
+    const float dc = dhn * (1.f - u);
+    const float dpc = dc * (1.f - c * c);
+    const float dp = dpc * r;
+    const float dr = dpc * p;
+    const float dgr = dr * r * (1.f - r);
+    const float dgu = du * u * (1.f - u);
+    const long long row3 = (long long)b * 3 * D;
+    a.dG[row3 + j] = dgr; a.dG[row3 + D + j] = dgu; a.dG[row3 + 2 * D + j] = dp;
+    a.dGx[row3 + j] = dgr; a.dGx[row3 + D + j] = dgu; a.dGx[row3 + 2 * D + j] = dpc;
+    a.dh_elem[idx] = (1.f - m) * dh + dhn * u;
+}
+
+// ------------------------------------------------------------------ small elementwise
+__global__ void tanh_inplace_kernel(float* x, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] = tanhf(x[i]);
+}
+__global__ void dtanh_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ dst,
+                             long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float t = y[i];
+        dst[i] = g[i] * (1.f - t * t);
+    }
+}
+__global__ void sum_parts_dtanh_kernel(const float* __restrict__ a, const float* __restrict__ part, int nsplit,
+                                       long long part_stride, const float* __restrict__ y, float* __restrict__ dst,
+                                       int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = a ? a[i] : 0.f;
+    for (int k = 0; k < nsplit; ++k) s += part[k * part_stride + i];
+    const float t = y[i];
+    dst[i] = s * (1.f - t * t);
+}
+__global__ void mask_lengths_kernel(const float* __restrict__ mask, int Tx, int B, float* __restrict__ xlen,
+                                    float* __restrict__ inv) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float s = 0.f;
+    if (mask) { for (int t = 0; t < Tx; ++t) s += mask[(long long)t * B + b]; }
+    else s = (float)Tx;
+    xlen[b] = s;
+    inv[b] = 1.f / s;
+}
+__global__ void scale_rows_kernel(const float* __restrict__ src, const float* __restrict__ inv, int B, int C,
+                                  float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    out[i] = src[i] * inv[i / C];
+}
+
+// column sums: stage 1 -> part[ks][N], stage 2 -> out
+template <bool PROD>
+__global__ void colsum_stage1(const float* __restrict__ X, const float* __restrict__ Y, long long K, int N, int ld,
+                              long long rows_per, float* __restrict__ part) {
+    __shared__ float red[8][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    const long long k0 = blockIdx.y * rows_per;
+    const long long k1 = (k0 + rows_per < K) ? (k0 + rows_per) : K;
+    float s = 0.f;
+    if (n < N) {
+        for (long long k = k0 + threadIdx.y; k < k1; k += 8) {
+            const float x = X[k * ld + n];
+            s += PROD ? x * Y[k * ld + n] : x;
+        }
+    }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        part[(long long)blockIdx.y * N + n] = t;
+    }
+}
+__global__ void colsum_stage2(const float* __restrict__ part, int ks, int N, float* __restrict__ out, int accumulate) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int i = 0; i < ks; ++i) s += part[(long long)i * N + n];
+    out[n] = accumulate ? out[n] + s : s;
+}
+
+__global__ void cost_reduce_kernel(const float* __restrict__ rowcost, int Ty, int B, float* __restrict__ cost,
+                                   float scale, float* __restrict__ total) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float s = 0.f;
+        for (int t = 0; t < Ty; ++t) s += rowcost[(long long)t * B + b];
+        if (cost) cost[b] = s;
+        acc += s;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0 && total) *total = acc * scale;
+}
+
+inline int grid_for(long long n, int block) {
+    long long g = (n + block - 1) / block;
+    if (g > 148LL * 32) g = 148LL * 32;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+int gather_rows(cudaStream_t st, const float* Wemb, const int64_t* ids, int n_rows, int W, int V, int shift,
+                float* out) {
+    const long long total = (long long)n_rows * W;
+    if (total == 0) return 0;
+    gather_rows_kernel<<<grid_for(total, 256), 256, 0, st>>>(Wemb, ids, n_rows, W, V, shift, out);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+int scatter_add_rows(cudaStream_t st, float* dWemb, const int64_t* ids, int n_rows, int W, int V, int shift,
+                     const float* src) {
+    const long long total = (long long)n_rows * W;
+    if (total == 0) return 0;
+    scatter_add_rows_kernel<<<grid_for(total, 256), 256, 0, st>>>(dWemb, ids, n_rows, W, V, shift, src);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+
+int gru_gates_fwd(cudaStream_t st, const GateFwd* groups, int ngroups, int B, int D, int mode) {
+    NATS_REQUIRE(ngroups >= 1 && ngroups <= 2, "gate groups");
+    GateFwdPack pack;
+    memset(&pack, 0, sizeof(pack));
+    for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
+    dim3 grid(cdiv(B * D, 256), ngroups);
+    if (mode == 0) gru_gates_fwd_kernel<0><<<grid, 256, 0, st>>>(pack, B, D);
+    else gru_gates_fwd_kernel<1><<<grid, 256, 0, st>>>(pack, B, D);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, int D) {
+    NATS_REQUIRE(ngroups >= 1 && ngroups <= 2, "gate groups");
+    GateBwdPack pack;
+    memset(&pack, 0, sizeof(pack));
+    for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
+    dim3 grid(cdiv(B * D, 256), ngroups);
+    gru_gates_bwd_kernel<<<grid, 256, 0, st>>>(pack, B, D);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+
+int tanh_inplace(cudaStream_t st, float* x, long long n) {
+    if (n == 0) return 0;
+    tanh_inplace_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, n);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+int dtanh(cudaStream_t st, const float* g, const float* y, float* dst, long long n) {
+    if (n == 0) return 0;
+    dtanh_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, y, dst, n);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+int sum_parts_dtanh(cudaStream_t st, const float* a, const float* part, int nsplit, long long part_stride,
+                    const float* y, float* dst, int B, int D) {
+    const int n = B * D;
+    sum_parts_dtanh_kernel<<<cdiv(n, 256), 256, 0, st>>>(a, part, nsplit, part_stride, y, dst, n);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+int mask_lengths(cudaStream_t st, const float* mask, int Tx, int B, float* xlen, float* inv) {
+    mask_lengths_kernel<<<cdiv(B, 128), 128, 0, st>>>(mask, Tx, B, xlen, inv);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+int scale_rows(cudaStream_t st, const float* src, const float* inv, int B, int C, float* out) {
+    scale_rows_kernel<<<cdiv(B * C, 256), 256, 0, st>>>(src, inv, B, C, out);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+
+static int colsum_impl(cudaStream_t st, const float* X, const float* Y, long long K, int N, int ld, float* out,
+                       int accumulate, float* scratch) {
+    if (N == 0) return 0;
+    int ks = (int)((K + 255) / 256);
+    if (ks > 64) ks = 64;
+    if (ks < 1) ks = 1;
+    const long long rows_per = (K + ks - 1) / ks;
+    dim3 grid(cdiv(N, 32), ks), block(32, 8);
+    if (Y) colsum_stage1<true><<<grid, block, 0, st>>>(X, Y, K, N, ld, rows_per, scratch);
+    else colsum_stage1<false><<<grid, block, 0, st>>>(X, nullptr, K, N, ld, rows_per, scratch);
+    NATS_LAUNCH_OK();
+    colsum_stage2<<<cdiv(N, 256), 256, 0, st>>>(scratch, ks, N, out, accumulate);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+int colsum(cudaStream_t st, const float* X, long long K, int N, int ld, float* out, int accumulate, float* scratch) {
+    return colsum_impl(st, X, nullptr, K, N, ld, out, accumulate, scratch);
+}
+int colsum_prod(cudaStream_t st, const float* X, const float* Y, long long K, int N, int ld, float* out,
+                int accumulate, float* scratch) {
+    return colsum_impl(st, X, Y, K, N, ld, out, accumulate, scratch);
+}
+int cost_reduce(cudaStream_t st, const float* rowcost, int Ty, int B, float* cost, float scale, float* total) {
+    cost_reduce_kernel<<<1, 256, 0, st>>>(rowcost, Ty, B, cost, scale, total);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace nats

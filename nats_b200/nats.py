@@ -1,0 +1,1073 @@
+"""
+nats_b200.nats -- host side of the B200 implementation of lukecq1231/nats' hot path.
+
+Same public surface as the reference's scripts/nats.py so that its drivers (train_nats.py, gen.py) keep working:
+
+    init_params, init_tparams, load_params, zipp, unzip, itemlist, prepare_data,
+    build_model, build_sampler, gen_sample, pred_probs, adadelta / adam / rmsprop / sgd, train
+
+but there is no Theano graph underneath: every compiled callable of the reference (f_init, f_next, f_log_probs,
+f_cost, f_grad_shared, f_update -- nats.py:817, 871, 1320, 1336, 1160, 1170) is a thin Python closure over
+libnats_b200.so (include/nats_b200.h), called through ctypes with raw device pointers.  PyTorch is used as the
+container for device memory, streams, CUDA graphs and NCCL only.
+
+There is no CPU fallback: without the CUDA library and a B200 the compiled callables raise NatsB200Error.
+Pure-host helpers (init_params, prepare_data, load_params, the beam bookkeeping of gen_sample) work anywhere.
+"""
+from collections import OrderedDict
+import copy
+import ctypes
+import logging
+import os
+import pickle as pkl
+import pprint
+import sys
+import time
+import warnings
+
+import numpy
+
+from . import _lib
+from ._lib import Dims, NatsB200Error
+from .data_iterator import TextIterator
+
+logger = logging.getLogger(__name__)
+profile = False
+
+
+# ----------------------------------------------------------------------------------------------------------
+# parameter dictionaries (reference: nats.py:31-46, 66-89, 118-142, 251-260, 271-302, 378-451, 613-654)
+# ----------------------------------------------------------------------------------------------------------
+def zipp(params, tparams):
+    """push host arrays into the device store (nats.py:31-33)"""
+    for kk, vv in params.items():
+        tparams[kk].set_value(vv)
+
+
+def unzip(zipped):
+    """pull the device store into host arrays (nats.py:37-41)"""
+    return OrderedDict((kk, vv.get_value()) for kk, vv in zipped.items())
+
+
+def itemlist(tparams):
+    return [vv for _, vv in tparams.items()]
+
+
+def _p(pp, name):
+    return '%s_%s' % (pp, name)
+
+
+def ortho_weight(ndim):
+    W = numpy.random.randn(ndim, ndim)
+    u, _, _ = numpy.linalg.svd(W)
+    return u.astype('float32')
+
+
+def norm_weight(nin, nout=None, scale=0.01, ortho=True):
+    if nout is None:
+        nout = nin
+    if nout == nin and ortho:
+        return ortho_weight(nin)
+    return (scale * numpy.random.randn(nin, nout)).astype('float32')
+
+
+def param_init_fflayer(options, params, prefix='ff', nin=None, nout=None, ortho=True):
+    nin = options['dim_proj'] if nin is None else nin
+    nout = options['dim_proj'] if nout is None else nout
+    params[_p(prefix, 'W')] = norm_weight(nin, nout, scale=0.01, ortho=ortho)
+    params[_p(prefix, 'b')] = numpy.zeros((nout,), dtype='float32')
+    return params
+
+
+def param_init_gru(options, params, prefix='gru', nin=None, dim=None):
+    nin = options['dim_proj'] if nin is None else nin
+    dim = options['dim_proj'] if dim is None else dim
+    params[_p(prefix, 'W')] = numpy.concatenate([norm_weight(nin, dim), norm_weight(nin, dim)], axis=1)
+    params[_p(prefix, 'b')] = numpy.zeros((2 * dim,), dtype='float32')
+    params[_p(prefix, 'U')] = numpy.concatenate([ortho_weight(dim), ortho_weight(dim)], axis=1)
+    params[_p(prefix, 'Wx')] = norm_weight(nin, dim)
+    params[_p(prefix, 'bx')] = numpy.zeros((dim,), dtype='float32')
+    params[_p(prefix, 'Ux')] = ortho_weight(dim)
+    return params
+
+
+def param_init_gru_cond(options, params, prefix='gru_cond', nin=None, dim=None, dimctx=None, dimatt=None):
+    nin = options['dim'] if nin is None else nin
+    dim = options['dim'] if dim is None else dim
+    dimctx = options['dim'] if dimctx is None else dimctx
+    dimatt = options['dim'] if dimatt is None else dimatt
+    z = lambda *s: numpy.zeros(s, dtype='float32')
+    # GRU_2 (previous state -> intermediate state), input = target embedding
+    params[_p(prefix, 'W')] = numpy.concatenate([norm_weight(nin, dim), norm_weight(nin, dim)], axis=1)
+    params[_p(prefix, 'U')] = numpy.concatenate([ortho_weight(dim), ortho_weight(dim)], axis=1)
+    params[_p(prefix, 'b')] = z(2 * dim)
+    params[_p(prefix, 'Wx')] = norm_weight(nin, dim)
+    params[_p(prefix, 'Ux')] = ortho_weight(dim)
+    params[_p(prefix, 'bx')] = z(dim)
+    # GRU_1 (intermediate state -> new state), input = context vector
+    params[_p(prefix, 'U_1')] = numpy.concatenate([ortho_weight(dim), ortho_weight(dim)], axis=1)
+    params[_p(prefix, 'W_1')] = norm_weight(dimctx, dim * 2)
+    params[_p(prefix, 'b_1')] = z(2 * dim)
+    params[_p(prefix, 'Wx_1')] = norm_weight(dimctx, dim)
+    params[_p(prefix, 'Ux_1')] = ortho_weight(dim)
+    params[_p(prefix, 'bx_1')] = z(dim)
+    # attention MLP
+    params[_p(prefix, 'W_att')] = norm_weight(dim, dimatt)
+    params[_p(prefix, 'Wc_att')] = norm_weight(dimctx, dimatt)
+    params[_p(prefix, 'b_att')] = z(dimatt)
+    params[_p(prefix, 'U_att')] = norm_weight(dimatt, 1)
+    params[_p(prefix, 'c_att')] = z(1)
+    # distraction: over context vectors (W_con, U_con) and over attention weights (D_wei)
+    params[_p(prefix, 'W_con')] = norm_weight(dimctx, 1)
+    params[_p(prefix, 'U_con')] = norm_weight(dimctx, 1)
+    params[_p(prefix, 'D_wei')] = norm_weight(1, dimatt)
+    return params
+
+
+layers = {'ff': ('param_init_fflayer', 'fflayer'),
+          'gru': ('param_init_gru', 'gru_layer'),
+          'gru_cond': ('param_init_gru_cond', 'gru_cond_layer')}
+
+
+def _layer_is_fused(*_a, **_k):
+    raise NatsB200Error('layer feed-forward functions are fused into libnats_b200 kernels; use build_model / '
+                        'build_sampler')
+
+
+fflayer = gru_layer = gru_cond_layer = _layer_is_fused
+
+
+def get_layer(name):
+    fns = layers[name]
+    return (globals()[fns[0]], globals()[fns[1]])
+
+
+def init_params(options):
+    """The 43 tensors in the reference's order (nats.py:613-654); numpy's global RNG, like the reference."""
+    if options.get('encoder', 'gru') != 'gru' or options.get('decoder', 'gru_cond') != 'gru_cond':
+        raise ValueError("only encoder='gru', decoder='gru_cond' exist (as in the reference's layer registry)")
+    params = OrderedDict()
+    params['Wemb'] = norm_weight(options['n_words'], options['dim_word'])
+    params = param_init_gru(options, params, prefix='encoder', nin=options['dim_word'], dim=options['dim'])
+    params = param_init_gru(options, params, prefix='encoder_r', nin=options['dim_word'], dim=options['dim'])
+    ctxdim = 2 * options['dim']
+    params = param_init_fflayer(options, params, prefix='ff_state', nin=ctxdim, nout=options['dim'])
+    params = param_init_gru_cond(options, params, prefix='decoder', nin=options['dim_word'], dim=options['dim'],
+                                 dimctx=ctxdim, dimatt=options['dim_att'])
+    params = param_init_fflayer(options, params, prefix='ff_logit_lstm', nin=options['dim'],
+                                nout=options['dim_word'], ortho=False)
+    params = param_init_fflayer(options, params, prefix='ff_logit_prev', nin=options['dim_word'],
+                                nout=options['dim_word'], ortho=False)
+    params = param_init_fflayer(options, params, prefix='ff_logit_ctx', nin=ctxdim, nout=options['dim_word'],
+                                ortho=False)
+    params = param_init_fflayer(options, params, prefix='ff_logit', nin=options['dim_word'],
+                                nout=options['n_words'])
+    return params
+
+
+def load_params(path, params):
+    """nats.py:81-89: fill `params` from an .npz archive, warn on (and skip) missing keys."""
+    pp = numpy.load(path, allow_pickle=True)
+    for kk in list(params.keys()):
+        if kk not in pp:
+            warnings.warn('%s is not in the archive' % kk)
+            continue
+        params[kk] = pp[kk]
+    return params
+
+
+def prepare_data(seqs_x, seqs_y, maxlen=None, n_words=30000):
+    """Batch layout contract of the hot path (nats.py:200-247): long sequences are cut to maxlen-1 tokens,
+    arrays are time-major and zero padded, masks carry len+1 ones (the implicit EOS row)."""
+    def clip(seqs):
+        if maxlen is None:
+            return list(seqs)
+        return [s[:maxlen - 1] if len(s) >= maxlen else s for s in seqs]
+    seqs_x, seqs_y = clip(seqs_x), clip(seqs_y)
+    if maxlen is not None and (len(seqs_x) < 1 or len(seqs_y) < 1):
+        return None, None, None, None
+    lx = [len(s) for s in seqs_x]
+    ly = [len(s) for s in seqs_y]
+    n_samples = len(seqs_x)
+    x = numpy.zeros((max(lx) + 1, n_samples), dtype='int64')
+    y = numpy.zeros((max(ly) + 1, n_samples), dtype='int64')
+    x_mask = numpy.zeros(x.shape, dtype='float32')
+    y_mask = numpy.zeros(y.shape, dtype='float32')
+    for idx in range(n_samples):
+        x[:lx[idx], idx] = seqs_x[idx]
+        x_mask[:lx[idx] + 1, idx] = 1.
+        y[:ly[idx], idx] = seqs_y[idx]
+        y_mask[:ly[idx] + 1, idx] = 1.
+    return x, x_mask, y, y_mask
+
+
+# ----------------------------------------------------------------------------------------------------------
+# device store: the replacement of theano.shared (nats.py:72-77)
+# ----------------------------------------------------------------------------------------------------------
+def _dims_from_shapes(shapes):
+    V, W = shapes['Wemb']
+    D = shapes['encoder_Ux'][0]
+    A = shapes['decoder_W_att'][1]
+    return int(V), int(W), int(D), int(A)
+
+
+class DeviceParam(object):
+    """One reference-named tensor living inside the flat device buffer (a strided view of the packed layout).
+    Offers the two methods the reference uses on shared variables: get_value / set_value."""
+
+    def __init__(self, store, name, offset, rows, cols, ld, ndim):
+        self.store, self.name = store, name
+        self.offset, self.rows, self.cols, self.ld, self.ndim = offset, rows, cols, ld, ndim
+
+    @property
+    def shape(self):
+        return (self.cols,) if self.ndim == 1 else (self.rows, self.cols)
+
+    def _view(self, flat):
+        return flat.as_strided((self.rows, self.cols), (self.ld, 1), self.offset)
+
+    def get_value(self, borrow=False):
+        arr = self._view(self.store.flat).cpu().numpy()
+        return arr.reshape(self.shape).copy()
+
+    def set_value(self, value, borrow=False):
+        import torch
+        value = numpy.ascontiguousarray(numpy.asarray(value, dtype='float32')).reshape(self.rows, self.cols)
+        self._view(self.store.flat).copy_(torch.from_numpy(value))
+
+    def __repr__(self):
+        return '<DeviceParam %s %s>' % (self.name, self.shape)
+
+
+class TParams(OrderedDict):
+    """OrderedDict name -> DeviceParam (reference order) + the flat device buffer they live in."""
+
+    def __init__(self, dims, engine):
+        super(TParams, self).__init__()
+        import torch
+        self.dims = dims                      # (V, W, D, A)
+        self.engine = engine
+        views, total = _lib.param_layout(*dims)
+        self.total = total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=engine.device)
+        for (name, off, rows, cols, ld, ndim) in views:
+            OrderedDict.__setitem__(self, name, DeviceParam(self, name, off, rows, cols, ld, ndim))
+
+    def view_of(self, flat_like):
+        """dict name -> host array for another flat buffer with the same layout (gradients, optimiser state)"""
+        return OrderedDict((k, v._view(flat_like).cpu().numpy().reshape(v.shape).copy()) for k, v in self.items())
+
+
+def init_tparams(params, engine=None):
+    """numpy dict -> device store (nats.py:72-77).  Needs a B200; prints 'name shape' like the reference."""
+    shapes = OrderedDict((k, numpy.shape(v)) for k, v in params.items())
+    dims = _dims_from_shapes(shapes)
+    engine = engine or get_engine()
+    tparams = TParams(dims, engine)
+    if list(tparams.keys()) != list(params.keys()):
+        raise ValueError('parameter names/order differ from the reference layout (nats.py:613-654)')
+    for kk, pp in params.items():
+        if tuple(tparams[kk].shape) != tuple(numpy.shape(pp)):
+            raise ValueError('%s: shape %s, expected %s' % (kk, numpy.shape(pp), tparams[kk].shape))
+        tparams[kk].set_value(pp)
+        print(kk, numpy.shape(pp))
+    return tparams
+
+
+# ----------------------------------------------------------------------------------------------------------
+# engine: context handle, workspaces, CUDA graphs
+# ----------------------------------------------------------------------------------------------------------
+_ENGINE = None
+
+
+def get_engine():
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine()
+    return _ENGINE
+
+
+class Engine(object):
+    def __init__(self, device_index=None):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise NatsB200Error('no CUDA device visible: nats_b200 runs on B200 (sm_100a) only, there is no CPU path')
+        if device_index is None:
+            device_index = int(os.environ.get('LOCAL_RANK', torch.cuda.current_device()))
+        torch.cuda.set_device(device_index)
+        self.device = torch.device('cuda', device_index)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.nats_ctx_create(device_index, ctypes.byref(h)), 'nats_ctx_create')
+        self.ctx = h
+        self.launches = 0          # C-ABI calls issued (each one enqueues many kernels)
+        self._ws = {}
+
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def workspace(self, key, nbytes):
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            self._ws[key] = None
+            t = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+            self._ws[key] = t
+        return t
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class _TrainPlan(object):
+    """Everything bound to one (Tx, Ty, B) shape: static input buffers, workspace, optional CUDA graph."""
+
+    def __init__(self, model, Tx, Ty, B):
+        torch = model.engine.torch
+        eng = model.engine
+        self.shape = (Tx, Ty, B)
+        dev = eng.device
+        self.x = torch.zeros((Tx, B), dtype=torch.int64, device=dev)
+        self.y = torch.zeros((Ty, B), dtype=torch.int64, device=dev)
+        self.xm = torch.zeros((Tx, B), dtype=torch.float32, device=dev)
+        self.ym = torch.zeros((Ty, B), dtype=torch.float32, device=dev)
+        self.hx = torch.zeros((Tx, B), dtype=torch.int64).pin_memory()
+        self.hy = torch.zeros((Ty, B), dtype=torch.int64).pin_memory()
+        self.hxm = torch.zeros((Tx, B), dtype=torch.float32).pin_memory()
+        self.hym = torch.zeros((Ty, B), dtype=torch.float32).pin_memory()
+        self.cost = torch.zeros((B,), dtype=torch.float32, device=dev)
+        nbytes = eng.lib.nats_train_workspace_bytes(ctypes.byref(model.dims), Tx, Ty, B)
+        if nbytes <= 0:
+            raise NatsB200Error('nats_train_workspace_bytes failed')
+        self.ws_bytes = int(nbytes)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.graph_fwd = None      # forward only (f_log_probs)
+        self.graph_fb = None       # forward + backward (data-parallel: the allreduce sits between fb and post)
+        self.graph_post = None     # L2 / clip / optimiser accumulators
+        self.graph_step = None     # single GPU: fb + post in one graph
+        self.uses = 0
+
+    def stage(self, x, x_mask, y, y_mask):
+        import torch as _t
+        self.hx.copy_(_t.from_numpy(numpy.ascontiguousarray(x, dtype='int64')))
+        self.hxm.copy_(_t.from_numpy(numpy.ascontiguousarray(x_mask, dtype='float32')))
+        self.hy.copy_(_t.from_numpy(numpy.ascontiguousarray(y, dtype='int64')))
+        self.hym.copy_(_t.from_numpy(numpy.ascontiguousarray(y_mask, dtype='float32')))
+        self.x.copy_(self.hx, non_blocking=True)
+        self.xm.copy_(self.hxm, non_blocking=True)
+        self.y.copy_(self.hy, non_blocking=True)
+        self.ym.copy_(self.hym, non_blocking=True)
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.hx, self.hxm, self.hy, self.hym))
+
+
+class ModelGraph(object):
+    """What build_model returns in place of the symbolic `cost` (nats.py:772): the training graph bound to a
+    device store.  f_log_probs / f_cost / gradients are produced from it by train() and the optimiser factories."""
+
+    MAX_PLANS = 4
+
+    def __init__(self, tparams, options):
+        self.tparams = tparams
+        self.engine = tparams.engine
+        self.options = options
+        V, W, D, A = tparams.dims
+        self.dims = Dims(V, W, D, A)
+        self.decay_c = 0.
+        self.clip_c = -1.
+        self.is_mean = False
+        self._plans = OrderedDict()
+        self.use_graphs = os.environ.get('NATS_CUDA_GRAPHS', '1') != '0'
+        torch = self.engine.torch
+        self.grads = torch.zeros(tparams.total + _lib.GRAD_TAIL, dtype=torch.float32, device=self.engine.device)
+        self.stats = torch.zeros(8, dtype=torch.float32, device=self.engine.device)
+        self.world = 1
+        self.rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
+            self.rank = torch.distributed.get_rank()
+
+    # -- reference idiom: cost = cost.mean() (nats.py:1323)
+    def mean(self):
+        g = copy.copy(self)
+        g.is_mean = True
+        return g
+
+    def plan(self, Tx, Ty, B):
+        key = (Tx, Ty, B)
+        p = self._plans.get(key)
+        if p is None:
+            while len(self._plans) >= self.MAX_PLANS:
+                self._plans.popitem(last=False)
+            p = _TrainPlan(self, Tx, Ty, B)
+            self._plans[key] = p
+        else:
+            self._plans.move_to_end(key)
+        return p
+
+    # -- raw enqueue helpers (no host sync)
+    def enqueue_fwd(self, p):
+        eng = self.engine
+        Tx, Ty, B = p.shape
+        _lib.check(eng.lib.nats_train_fwd(eng.ctx, eng.stream(), ctypes.byref(self.dims), _ptr(self.tparams.flat),
+                                          _ptr(p.x), _ptr(p.xm), _ptr(p.y), _ptr(p.ym), Tx, Ty, B, _ptr(p.ws),
+                                          p.ws_bytes, _ptr(p.cost)), 'nats_train_fwd')
+        eng.launches += 1
+
+    def enqueue_bwd(self, p, scale):
+        eng = self.engine
+        Tx, Ty, B = p.shape
+        _lib.check(eng.lib.nats_train_bwd(eng.ctx, eng.stream(), ctypes.byref(self.dims), _ptr(self.tparams.flat),
+                                          _ptr(p.x), _ptr(p.xm), _ptr(p.y), _ptr(p.ym), Tx, Ty, B, _ptr(p.ws),
+                                          p.ws_bytes, ctypes.c_float(scale), _ptr(self.grads)), 'nats_train_bwd')
+        eng.launches += 1
+
+    def enqueue_clip(self):
+        eng = self.engine
+        _lib.check(eng.lib.nats_grad_clip(eng.ctx, eng.stream(), self.tparams.total, _ptr(self.tparams.flat),
+                                          _ptr(self.grads), ctypes.c_float(self.decay_c),
+                                          ctypes.c_float(self.clip_c), _ptr(self.stats)), 'nats_grad_clip')
+        eng.launches += 1
+
+    def _run(self, p, attr, body):
+        """run `body` eagerly the first two times a shape is seen, then capture + replay it as a CUDA graph"""
+        torch = self.engine.torch
+        g = getattr(p, attr)
+        if g is not None:
+            g.replay()
+            return
+        if self.use_graphs and p.uses >= 2:
+            torch.cuda.synchronize(self.engine.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            setattr(p, attr, g)
+            g.replay()
+            return
+        body()
+
+    # -- compiled callables
+    def f_log_probs(self, x, x_mask, y, y_mask):
+        """per-sample negative log-likelihood [B] (nats.py:1320)"""
+        p = self.plan(x.shape[0], y.shape[0], x.shape[1])
+        p.stage(x, x_mask, y, y_mask)
+        self._run(p, 'graph_fwd', lambda: self.enqueue_fwd(p))
+        p.uses += 1
+        return p.cost.cpu().numpy()
+
+    def f_cost(self, x, x_mask, y, y_mask):
+        """mean cost (+ L2) (nats.py:1323-1336)"""
+        c = float(self.f_log_probs(x, x_mask, y, y_mask).mean(dtype='float64'))
+        if self.decay_c > 0.:
+            c += self.decay_c * float((self.tparams.flat.double() ** 2).sum().item())
+        return numpy.float32(c)
+
+    def grad_step(self, x, x_mask, y, y_mask, after_grads):
+        """forward + backward (+ allreduce) + L2/clip + `after_grads()` (the optimiser's accumulator update);
+        returns the scalar cost like f_grad_shared (nats.py:1160)."""
+        torch = self.engine.torch
+        p = self.plan(x.shape[0], y.shape[0], x.shape[1])
+        p.stage(x, x_mask, y, y_mask)
+        B = x.shape[1]
+        scale = 1.0 / (B * self.world)        # d mean(cost) over the GLOBAL batch (nats.py:1323)
+
+        def fwd_bwd():
+            self.enqueue_fwd(p)
+            self.enqueue_bwd(p, scale)
+
+        def post():
+            self.enqueue_clip()
+            after_grads()
+
+        if self.world == 1:
+            self._run(p, 'graph_step', lambda: (fwd_bwd(), post()))
+        else:
+            self._run(p, 'graph_fb', fwd_bwd)
+            torch.distributed.all_reduce(self.grads)          # ONE collective: gradients + cost tail
+            self._run(p, 'graph_post', post)
+        p.uses += 1
+        cost = float(self.grads[self.tparams.total].item())   # device->host read of the step result
+        if self.decay_c > 0.:
+            cost += self.decay_c * float(self.stats[1].item())
+        return numpy.float32(cost)
+
+
+def build_model(tparams, options):
+    """Reference signature (nats.py:658-772).  Returns the same 8-tuple; the symbolic inputs are replaced by
+    their names and `cost` by a ModelGraph bound to `tparams`."""
+    opt_ret = dict()
+    trng = numpy.random.RandomState(1234)
+    use_noise = _HostFlag(0.)
+    graph = ModelGraph(tparams, options)
+    return trng, use_noise, 'x', 'x_mask', 'y', 'y_mask', opt_ret, graph
+
+
+class _HostFlag(object):
+    def __init__(self, v):
+        self.v = v
+
+    def set_value(self, v):
+        self.v = v
+
+    def get_value(self):
+        return self.v
+
+
+# ----------------------------------------------------------------------------------------------------------
+# optimisers: name(lr, tparams, grads, inp, cost) -> (f_grad_shared, f_update)   (nats.py:1104-1221)
+# `grads` is the ModelGraph (it owns the flat gradient buffer; clipping / L2 were configured on it by train()).
+# ----------------------------------------------------------------------------------------------------------
+def _zeros_like_flat(graph):
+    torch = graph.engine.torch
+    return torch.zeros(graph.tparams.total, dtype=torch.float32, device=graph.engine.device)
+
+
+def adadelta(lr, tparams, grads, inp, cost, epsilon=1e-6, rho=0.95):
+    graph = grads
+    eng = graph.engine
+    running_up2, running_grads2 = _zeros_like_flat(graph), _zeros_like_flat(graph)
+    n = tparams.total
+
+    def accum():
+        _lib.check(eng.lib.nats_adadelta_grad_shared(eng.ctx, eng.stream(), n, _ptr(graph.grads),
+                                                     _ptr(running_grads2), ctypes.c_float(rho)),
+                   'nats_adadelta_grad_shared')
+        eng.launches += 1
+
+    def f_grad_shared(x, x_mask, y, y_mask):
+        return graph.grad_step(x, x_mask, y, y_mask, accum)
+
+    def f_update(lr_value=None):
+        _lib.check(eng.lib.nats_adadelta_update(eng.ctx, eng.stream(), n, _ptr(tparams.flat), _ptr(graph.grads),
+                                                _ptr(running_up2), _ptr(running_grads2), ctypes.c_float(rho),
+                                                ctypes.c_float(epsilon)), 'nats_adadelta_update')
+        eng.launches += 1
+        return []
+
+    f_grad_shared.state = dict(running_up2=running_up2, running_grads2=running_grads2)
+    return f_grad_shared, f_update
+
+
+def adam(lr, tparams, grads, inp, cost):
+    graph = grads
+    eng = graph.engine
+    m, v = _zeros_like_flat(graph), _zeros_like_flat(graph)
+    n = tparams.total
+    step = [0]
+
+    def f_grad_shared(x, x_mask, y, y_mask):
+        return graph.grad_step(x, x_mask, y, y_mask, lambda: None)
+
+    def f_update(lr_value=None):
+        _lib.check(eng.lib.nats_adam_update(eng.ctx, eng.stream(), n, _ptr(tparams.flat), _ptr(graph.grads),
+                                            _ptr(m), _ptr(v), step[0]), 'nats_adam_update')
+        eng.launches += 1
+        step[0] += 1
+        return []
+
+    f_grad_shared.state = dict(m=m, v=v)
+    return f_grad_shared, f_update
+
+
+def rmsprop(lr, tparams, grads, inp, cost):
+    graph = grads
+    eng = graph.engine
+    rg, rg2, ud = _zeros_like_flat(graph), _zeros_like_flat(graph), _zeros_like_flat(graph)
+    n = tparams.total
+
+    def accum():
+        _lib.check(eng.lib.nats_rmsprop_grad_shared(eng.ctx, eng.stream(), n, _ptr(graph.grads), _ptr(rg),
+                                                    _ptr(rg2)), 'nats_rmsprop_grad_shared')
+        eng.launches += 1
+
+    def f_grad_shared(x, x_mask, y, y_mask):
+        return graph.grad_step(x, x_mask, y, y_mask, accum)
+
+    def f_update(lr_value=None):
+        _lib.check(eng.lib.nats_rmsprop_update(eng.ctx, eng.stream(), n, _ptr(tparams.flat), _ptr(graph.grads),
+                                               _ptr(ud), _ptr(rg), _ptr(rg2)), 'nats_rmsprop_update')
+        eng.launches += 1
+        return []
+
+    f_grad_shared.state = dict(running_grads=rg, running_grads2=rg2, updir=ud)
+    return f_grad_shared, f_update
+
+
+def sgd(lr, tparams, grads, inp, cost):
+    """The reference's sgd has a 7-argument signature that train() never matches (dead code, nats.py:1209);
+    provided here with the common 5-argument form: p <- p - lr * g."""
+    graph = grads
+
+    def f_grad_shared(x, x_mask, y, y_mask):
+        return graph.grad_step(x, x_mask, y, y_mask, lambda: None)
+
+    def f_update(lr_value):
+        tparams.flat.add_(graph.grads[:tparams.total], alpha=-float(lr_value))
+        return []
+
+    return f_grad_shared, f_update
+
+
+_OPTIMIZERS = {'adadelta': adadelta, 'adam': adam, 'rmsprop': rmsprop, 'sgd': sgd}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# sampler (nats.py:776-874)
+# ----------------------------------------------------------------------------------------------------------
+class DeviceBackedArray(numpy.ndarray):
+    """Host copy of an encoder context that remembers its device-resident original (and the projected context
+    pctx).  numpy.tile / broadcast_to keep the subclass, so f_next can recognise `tile(ctx0, [live_k, 1])`
+    (nats.py:958) and read the ONE device copy with a zero batch stride instead of re-uploading k copies."""
+
+    def __new__(cls, arr, handle=None):
+        obj = numpy.asarray(arr).view(cls)
+        obj._nats_handle = handle
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._nats_handle = getattr(obj, '_nats_handle', None)
+
+
+class _CtxHandle(object):
+    def __init__(self, ctx_dev, pctx_dev, host):
+        self.ctx_dev, self.pctx_dev, self.host = ctx_dev, pctx_dev, host
+        Tx = host.shape[0]
+        self.probe_t = numpy.unique(numpy.linspace(0, Tx - 1, num=min(Tx, 8)).astype('int64'))
+
+    def matches(self, ctx):
+        """is `ctx` [Tx,n,C] the broadcast of the single-sentence context this handle owns?"""
+        h = self.host
+        if h.shape[1] != 1 or ctx.ndim != 3 or ctx.shape[0] != h.shape[0] or ctx.shape[2] != h.shape[2]:
+            return False
+        a = numpy.asarray(ctx)[self.probe_t]
+        return bool(numpy.array_equal(a, numpy.broadcast_to(h[self.probe_t], a.shape)))
+
+
+def build_sampler(tparams, options, trng=None):
+    """-> f_init, f_next with the reference signatures (nats.py:817, 869-871)."""
+    eng = tparams.engine
+    torch = eng.torch
+    V, W, D, A = tparams.dims
+    C = 2 * D
+    dims = Dims(V, W, D, A)
+    seed = 1234
+    counter = [0]
+
+    def ws_for(Tx, n):
+        nbytes = eng.lib.nats_sampler_workspace_bytes(ctypes.byref(dims), Tx, n)
+        if nbytes <= 0:
+            raise NatsB200Error('nats_sampler_workspace_bytes failed')
+        return eng.workspace(('sampler',), nbytes), int(nbytes)
+
+    def f_init(x):
+        x = numpy.ascontiguousarray(x, dtype='int64')
+        Tx, n = x.shape
+        xd = torch.from_numpy(x).to(eng.device)
+        ws, nbytes = ws_for(Tx, n)
+        init_state = torch.empty((n, D), dtype=torch.float32, device=eng.device)
+        ctx = torch.empty((Tx, n, C), dtype=torch.float32, device=eng.device)
+        pctx = torch.empty((Tx, n, A), dtype=torch.float32, device=eng.device)
+        _lib.check(eng.lib.nats_sampler_init(eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(xd),
+                                             Tx, n, _ptr(ws), nbytes, _ptr(init_state), _ptr(ctx), _ptr(pctx)),
+                   'nats_sampler_init')
+        eng.launches += 1
+        host = ctx.cpu().numpy()
+        return [init_state.cpu().numpy(), DeviceBackedArray(host, _CtxHandle(ctx, pctx, host))]
+
+    def f_next(y, ctx, init_state, acc_ctx, acc_alpha):
+        y = numpy.ascontiguousarray(y, dtype='int64')
+        n = y.shape[0]
+        Tx = ctx.shape[0]
+        handle = getattr(ctx, '_nats_handle', None)
+        if handle is not None and handle.matches(ctx):
+            ctx_d, pctx_d = handle.ctx_dev, handle.pctx_dev
+            cts, cbs, pts, pbs = C, 0, A, 0                   # one source shared by all n hypotheses
+            pptr = _ptr(pctx_d)
+        else:                                                 # arbitrary context: upload, recompute pctx (nats.py:493)
+            ctx_d = torch.from_numpy(numpy.ascontiguousarray(ctx, dtype='float32')).to(eng.device)
+            if ctx_d.shape[1] != n:
+                raise ValueError('ctx has %d columns, y has %d' % (ctx_d.shape[1], n))
+            cts, cbs, pts, pbs = n * C, C, 0, 0
+            pptr = ctypes.c_void_p(0)
+        up = lambda a, shp: torch.from_numpy(numpy.ascontiguousarray(a, dtype='float32').reshape(shp)).to(eng.device)
+        yd = torch.from_numpy(y).to(eng.device)
+        st_d, ac_d, aa_d = up(init_state, (n, D)), up(acc_ctx, (n, C)), up(acc_alpha, (n, Tx))
+        ws, nbytes = ws_for(Tx, n)
+        f32 = dict(dtype=torch.float32, device=eng.device)
+        probs = torch.empty((n, V), **f32)
+        sample = torch.empty((n,), dtype=torch.int64, device=eng.device)
+        state_o, alphaT, ctxs = torch.empty((n, D), **f32), torch.empty((n, Tx), **f32), torch.empty((n, C), **f32)
+        acc_ctx_o, acc_alpha_o = torch.empty((n, C), **f32), torch.empty((n, Tx), **f32)
+        _lib.check(eng.lib.nats_sampler_next(
+            eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(yd), _ptr(ctx_d), cts, cbs, pptr,
+            pts, pbs, _ptr(st_d), _ptr(ac_d), _ptr(aa_d), Tx, n, seed, counter[0], _ptr(ws), nbytes, _ptr(probs),
+            _ptr(sample), _ptr(state_o), _ptr(alphaT), _ptr(ctxs), _ptr(acc_ctx_o), _ptr(acc_alpha_o)),
+            'nats_sampler_next')
+        eng.launches += 1
+        counter[0] += 1
+        f_next.last_device = dict(alpha=alphaT, ctx=ctxs, state=state_o)
+        return [probs.cpu().numpy(), sample.cpu().numpy(), state_o.cpu().numpy(), alphaT.cpu().numpy(),
+                ctxs.cpu().numpy(), acc_ctx_o.cpu().numpy(), acc_alpha_o.cpu().numpy()]
+
+    f_next.last_device = None
+    f_next.engine = eng
+    return f_init, f_next
+
+
+# ----------------------------------------------------------------------------------------------------------
+# beam search with distraction (nats.py:879-1076)
+# ----------------------------------------------------------------------------------------------------------
+class DistractionScorer(object):
+    """Device-resident attention / context / state histories of the live hypotheses and the lambda_1..3 penalties
+    of nats.py:981-995 computed by nats_beam_distraction_scores (replaces O(k*ii) SciPy calls per step)."""
+
+    def __init__(self, engine, k, maxlen, Tx, C, D):
+        torch = engine.torch
+        self.eng, self.k, self.cap = engine, k, maxlen
+        self.dims = (Tx, C, D)
+        mk = lambda d: [torch.zeros((k, maxlen, d), dtype=torch.float32, device=engine.device) for _ in range(2)]
+        self.hist = [mk(Tx), mk(C), mk(D)]       # [alpha, ctx, state] x ping-pong
+        self.cur = 0
+        self.len = 0
+        self.scratch = torch.zeros(3 * k * maxlen + 16, dtype=torch.float32, device=engine.device)
+        self.out = torch.zeros(3 * k, dtype=torch.float32, device=engine.device)
+
+    def _dev(self, arr):
+        torch = self.eng.torch
+        if isinstance(arr, torch.Tensor):
+            return arr
+        return torch.from_numpy(numpy.ascontiguousarray(arr, dtype='float32')).to(self.eng.device)
+
+    def penalties(self, cur_alpha, cur_ctx, cur_state, live_k, kl, cf, sf):
+        eng = self.eng
+        Tx, C, D = self.dims
+        a, c, s = self._dev(cur_alpha), self._dev(cur_ctx), self._dev(cur_state)
+        h = [self.hist[i][self.cur] for i in range(3)]
+        _lib.check(eng.lib.nats_beam_distraction_scores(
+            eng.ctx, eng.stream(), _ptr(h[0]), _ptr(h[1]), _ptr(h[2]), self.cap, self.len, live_k, Tx, C, D,
+            _ptr(a), _ptr(c), _ptr(s), ctypes.c_float(kl), ctypes.c_float(cf), ctypes.c_float(sf),
+            _ptr(self.scratch), _ptr(self.out)), 'nats_beam_distraction_scores')
+        eng.launches += 1
+        return self.out[:3 * live_k].cpu().numpy().reshape(3, live_k)
+
+    def advance(self, cur_alpha, cur_ctx, cur_state, parents):
+        """histories of the surviving hypotheses j <- history of parents[j] + the current step's vectors"""
+        eng = self.eng
+        torch = eng.torch
+        if len(parents) == 0:
+            return
+        par = torch.tensor(list(map(int, parents)), dtype=torch.int32, device=eng.device)
+        curs = [self._dev(cur_alpha), self._dev(cur_ctx), self._dev(cur_state)]
+        for i in range(3):
+            src, dst = self.hist[i][self.cur], self.hist[i][self.cur ^ 1]
+            _lib.check(eng.lib.nats_beam_reorder_append(eng.ctx, eng.stream(), _ptr(src), _ptr(dst), _ptr(curs[i]),
+                                                        _ptr(par), len(parents), self.cap, self.len, self.dims[i]),
+                       'nats_beam_reorder_append')
+            eng.launches += 1
+        self.cur ^= 1
+        self.len += 1
+
+
+def _tile_ctx(ctx0, live_k):
+    """numpy.tile(ctx0, [live_k, 1]) (nats.py:958) without materialising live_k copies"""
+    if ctx0.shape[1] == 1:
+        return numpy.broadcast_to(ctx0, (ctx0.shape[0], live_k, ctx0.shape[2]), subok=True)
+    return numpy.tile(ctx0, [live_k, 1])
+
+
+def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, stochastic=True, argmax=False,
+               use_unk=False, kl_factor=0, ctx_factor=0, state_factor=0, _scorer_factory=None):
+    """Stochastic sampling or beam search with distraction re-ranking; same arguments, return values and
+    hypothesis bookkeeping as the reference (nats.py:879-1076).  Candidate costs stay un-penalised (nats.py:1004);
+    the three penalties only re-rank (nats.py:997-999)."""
+    if k > 1:
+        assert not stochastic, 'Beam search does not support stochastic sampling'
+
+    sample, sample_score, sample_dec_alphas = [], [], []
+    if stochastic:
+        sample_score = 0
+
+    live_k, dead_k = 1, 0
+    hyp_samples = [[]]
+    hyp_scores = numpy.zeros(live_k, dtype='float32')
+    hyp_dec_alphas = [[]]
+
+    next_state, ctx0 = f_init(x)
+    next_w = -1 * numpy.ones((1,), dtype='int64')        # BOS marker -> zero embedding
+    acc_ctx = numpy.zeros((live_k, ctx0.shape[2]), dtype='float32')
+    acc_alpha = numpy.zeros((live_k, ctx0.shape[0]), dtype='float32')
+
+    distract = (not stochastic) and (kl_factor > 0. or ctx_factor > 0. or state_factor > 0.)
+    scorer = None
+    if distract:
+        if _scorer_factory is not None:
+            scorer = _scorer_factory(k, maxlen, ctx0.shape[0], ctx0.shape[2], next_state.shape[1])
+        else:
+            eng = getattr(f_next, 'engine', None) or get_engine()
+            scorer = DistractionScorer(eng, k, maxlen, ctx0.shape[0], ctx0.shape[2], next_state.shape[1])
+
+    for ii in range(maxlen):
+        ctx = _tile_ctx(ctx0, live_k)
+        next_p, next_w, next_state, dec_alphas, ctxs, acc_ctx, acc_alpha = f_next(next_w, ctx, next_state, acc_ctx,
+                                                                                  acc_alpha)
+        if stochastic:
+            nw = next_p[0].argmax() if argmax else next_w[0]
+            sample.append(nw)
+            sample_score += next_p[0, nw]
+            if nw == 0:
+                break
+            continue
+
+        dev = getattr(f_next, 'last_device', None) or {}
+        cur = (dev.get('alpha', dec_alphas), dev.get('ctx', ctxs), dev.get('state', next_state))
+        if not use_unk:
+            next_p[:, 1] = 1e-20
+        cand_scores = hyp_scores[:, None] - numpy.log(next_p)
+        cand_flat = cand_scores.flatten()
+        n_keep = k - dead_k
+        if distract and ii > 0:
+            pen = scorer.penalties(cur[0], cur[1], cur[2], live_k, kl_factor, ctx_factor, state_factor)
+            ranked = (cand_scores + pen[0][:, None] + pen[1][:, None] + pen[2][:, None]).flatten()
+            ranks_flat = ranked.argsort()[:n_keep]
+        else:
+            ranks_flat = cand_flat.argsort()[:n_keep]
+
+        voc_size = next_p.shape[1]
+        trans_indices = ranks_flat // voc_size
+        word_indices = ranks_flat % voc_size
+        costs = cand_flat[ranks_flat]
+
+        survivors = []                    # (parent index, word, cost) of the hypotheses that stay alive
+        for ti, wi, ci in zip(trans_indices, word_indices, costs):
+            grown = hyp_samples[ti] + [wi]
+            alphas = hyp_dec_alphas[ti] + [dec_alphas[ti].copy()]
+            if wi == 0:                   # finished: move to the result lists (nats.py:1037-1041)
+                sample.append(grown)
+                sample_score.append(numpy.float32(ci))
+                sample_dec_alphas.append(alphas)
+                dead_k += 1
+            else:
+                survivors.append((int(ti), grown, numpy.float32(ci), alphas))
+
+        live_k = len(survivors)
+        if live_k < 1 or dead_k >= k:
+            hyp_samples = [s[1] for s in survivors]
+            hyp_scores = numpy.array([s[2] for s in survivors], dtype='float32')
+            hyp_dec_alphas = [s[3] for s in survivors]
+            break
+        parents = [s[0] for s in survivors]
+        if distract:
+            scorer.advance(cur[0], cur[1], cur[2], parents)
+        hyp_samples = [s[1] for s in survivors]
+        hyp_scores = numpy.array([s[2] for s in survivors], dtype='float32')
+        hyp_dec_alphas = [s[3] for s in survivors]
+        next_w = numpy.array([w[-1] for w in hyp_samples], dtype='int64')
+        next_state = next_state[parents].copy()
+        acc_ctx = acc_ctx[parents].copy()
+        acc_alpha = acc_alpha[parents].copy()
+
+    if not stochastic and live_k > 0:     # dump what is still alive (nats.py:1068-1074)
+        for idx in range(live_k):
+            sample.append(hyp_samples[idx])
+            sample_score.append(hyp_scores[idx])
+            sample_dec_alphas.append(hyp_dec_alphas[idx])
+    return sample, sample_score, sample_dec_alphas
+
+
+# ----------------------------------------------------------------------------------------------------------
+# validation cost and the training loop (nats.py:1080-1101, 1230-1539)
+# ----------------------------------------------------------------------------------------------------------
+def pred_probs(f_log_probs, prepare_data, options, iterator, verbose=True):
+    probs = []
+    n_done = 0
+    for x, y in iterator:
+        n_done += len(x)
+        x, x_mask, y, y_mask = prepare_data(x, y, n_words=options['n_words'])
+        probs.extend(f_log_probs(x, x_mask, y, y_mask))
+        if numpy.isnan(numpy.mean(probs)):
+            raise FloatingPointError('NaN validation cost')      # the reference drops into pdb here (:1095)
+        if verbose:
+            print('%d samples computed' % n_done, file=sys.stderr)
+    return numpy.array(probs)
+
+
+def _load_pickle(path):
+    with open(path, 'rb') as f:
+        try:
+            return pkl.load(f)
+        except UnicodeDecodeError:          # python-2 pickles written by the reference (nats.py:1434)
+            f.seek(0)
+            return pkl.load(f, encoding='latin1')
+
+
+def _words(ids, worddicts_r):
+    out = []
+    for vv in ids:
+        if vv == 0:
+            break
+        out.append(worddicts_r.get(vv, 'UNK'))
+    return ' '.join(out)
+
+
+def train(dim_word=100, dim=1000, dim_att=100, encoder='gru', decoder='gru_cond', patience=10, max_epochs=5000,
+          finish_after=10000000, dispFreq=100, decay_c=0., clip_c=-1., lrate=0.01, n_words=100000, maxlen=100,
+          optimizer='adadelta', batch_size=16, valid_batch_size=16, saveto='model.npz', validFreq=1000,
+          saveFreq=1000, sampleFreq=100, datasets=[], valid_datasets=[], dictionary='', use_dropout=False,
+          reload_=False, verbose=False):
+    """Same keyword surface, side effects (npz + options pickle, log lines) and return value as the reference's
+    train() (nats.py:1230-1539)."""
+    logging.basicConfig(level=logging.DEBUG, format="%(asctime)s: %(name)s: %(levelname)s: %(message)s")
+    model_options = locals().copy()
+
+    worddicts = _load_pickle(dictionary)
+    worddicts_r = dict((vv, kk) for kk, vv in worddicts.items())
+
+    if reload_ and os.path.exists(saveto):
+        print('Reload options')
+        model_options = _load_pickle('%s.pkl' % saveto)
+    logger.debug(pprint.pformat(model_options))
+
+    print('Loading data')
+    train_it = TextIterator(datasets[0], datasets[1], dictionary, n_words=n_words, batch_size=batch_size)
+    valid_it = TextIterator(valid_datasets[0], valid_datasets[1], dictionary, n_words=n_words,
+                            batch_size=valid_batch_size)
+
+    print('Building model')
+    params = init_params(model_options)
+    if reload_ and os.path.exists(saveto):
+        print('Reload parameters')
+        params = load_params(saveto, params)
+    tparams = init_tparams(params)
+
+    trng, use_noise, x, x_mask, y, y_mask, opt_ret, cost = build_model(tparams, model_options)
+    inps = [x, x_mask, y, y_mask]
+    print('Buliding sampler')
+    f_init, f_next = build_sampler(tparams, model_options, trng)
+
+    print('Building f_log_probs...', end=' ')
+    f_log_probs = cost.f_log_probs
+    print('Done')
+    cost = cost.mean()
+    cost.decay_c = float(decay_c) if decay_c > 0. else 0.          # nats.py:1326-1332
+    print('Building f_cost...', end=' ')
+    f_cost = cost.f_cost                                           # noqa: F841 (compiled, unused: as the reference)
+    print('Done')
+    print('Computing gradient...', end=' ')
+    cost.clip_c = float(clip_c)                                    # nats.py:1344-1353
+    grads = cost
+    print('Done')
+
+    lr = 'lr'
+    print('Building optimizers...', end=' ')
+    f_grad_shared, f_update = _OPTIMIZERS[optimizer](lr, tparams, grads, inps, cost)
+    print('Done')
+    print('Optimization')
+
+    history_errs = []
+    if reload_ and os.path.exists(saveto):
+        print('Reload history error')
+        history_errs = list(numpy.load(saveto, allow_pickle=True)['history_errs'])
+    best_p = None
+    bad_counter = 0
+
+    if validFreq == -1 or saveFreq == -1 or sampleFreq == -1:
+        n_train = sum(1 for _ in open(datasets[0], 'r'))
+        per_epoch = max(1, n_train // batch_size)
+        validFreq = per_epoch if validFreq == -1 else validFreq
+        saveFreq = per_epoch if saveFreq == -1 else saveFreq
+        sampleFreq = per_epoch if sampleFreq == -1 else sampleFreq
+
+    uidx = 0
+    estop = False
+    for eidx in range(max_epochs):
+        n_samples = 0
+        for x, y in train_it:
+            n_samples += len(x)
+            uidx += 1
+            use_noise.set_value(1.)
+            x, x_mask, y, y_mask = prepare_data(x, y, maxlen=maxlen, n_words=n_words)
+            if x is None:
+                print('Minibatch with zero sample under length ', maxlen)
+                uidx -= 1
+                continue
+
+            ud_start = time.time()
+            cost_v = f_grad_shared(x, x_mask, y, y_mask)
+            if verbose and clip_c > 0.:
+                norm_g = float(numpy.sqrt(grads.stats[0].item()))
+            f_update(lrate)
+            ud = time.time() - ud_start
+
+            if numpy.isnan(cost_v) or numpy.isinf(cost_v):
+                print('NaN detected')
+                return 1., 1., 1.
+
+            if numpy.mod(uidx, dispFreq) == 0:
+                logger.debug('Epoch {0} Update {1} Cost {2} UD {3}'.format(eidx, uidx, cost_v, ud))
+                if verbose and clip_c > 0.:
+                    logger.debug('Grad {0}'.format(norm_g))
+
+            if numpy.mod(uidx, saveFreq) == 0:
+                print('Saving...', end=' ')
+                params = best_p if best_p is not None else unzip(tparams)
+                numpy.savez(saveto, history_errs=history_errs, **params)
+                with open('%s.pkl' % saveto, 'wb') as f:
+                    pkl.dump(model_options, f, protocol=2)
+                print('Done')
+
+            if numpy.mod(uidx, sampleFreq) == 0:
+                for jj in range(int(numpy.minimum(5, x.shape[1]))):
+                    sample, score, dec_alphas = gen_sample(tparams, f_init, f_next, x[:, jj][:, None], model_options,
+                                                           trng=trng, k=1, maxlen=30, stochastic=True, argmax=False)
+                    print('Source ', jj, ': ', _words(x[:, jj], worddicts_r))
+                    print('Truth ', jj, ' : ', _words(y[:, jj], worddicts_r))
+                    print('Sample ', jj, ': ', _words(sample, worddicts_r))
+
+            if numpy.mod(uidx, validFreq) == 0:
+                use_noise.set_value(0.)
+                valid_errs = pred_probs(f_log_probs, prepare_data, model_options, valid_it)
+                valid_err = valid_errs.mean()
+                history_errs.append(valid_err)
+                if uidx == 0 or valid_err <= numpy.array(history_errs).min():
+                    best_p = unzip(tparams)
+                    bad_counter = 0
+                if patience == 0:
+                    if len(history_errs) > 1 and valid_err >= numpy.array(history_errs)[:-1].min():
+                        print('Early Stop!')
+                        estop = True
+                        break
+                elif len(history_errs) > patience and valid_err >= numpy.array(history_errs)[:-patience].min():
+                    bad_counter += 1
+                    if bad_counter > patience:
+                        print('Early Stop!')
+                        estop = True
+                        break
+                if numpy.isnan(valid_err):
+                    raise FloatingPointError('NaN validation error')
+                print('Valid ', valid_err)
+
+            if uidx >= finish_after:
+                print('Finishing after %d iterations!' % uidx)
+                estop = True
+                break
+
+        print('Seen %d samples' % n_samples)
+        if estop:
+            break
+
+    if best_p is not None:
+        zipp(best_p, tparams)
+    use_noise.set_value(0.)
+    valid_err = pred_probs(f_log_probs, prepare_data, model_options, valid_it).mean()
+    print('Valid ', valid_err)
+
+    params = copy.copy(best_p) if best_p is not None else unzip(tparams)
+    numpy.savez(saveto, zipped_params=best_p, history_errs=history_errs, **params)
+    logger.debug('Done')
+    return valid_err
+
+
+if __name__ == '__main__':
+    pass

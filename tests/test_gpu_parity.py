@@ -1,0 +1,292 @@
+"""GPU parity: the CUDA path (through the C ABI, via nats_b200.nats) against the float64 oracle on the same
+seeded inputs, and against the committed golden fixtures.  Tolerances (fp32 FFMA path, stated per output):
+  per-sample cost   rel <= 1e-4        gradients  ||g-g*|| / ||g*|| <= 1e-3 per tensor (measured ~1e-6)
+  f_next probs      max abs <= 1e-5    beam search: identical token sequences
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nats_oracle as O
+from tests.helpers import toy_options, toy_params, ragged_batch, full_batch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.fixture(scope='module')
+def N():
+    from nats_b200 import nats
+    return nats
+
+
+def _setup(N, opts, P64):
+    tparams = N.init_tparams(O.cast_params(P64, 'float32'))
+    graph = N.build_model(tparams, opts)[-1]
+    return tparams, graph
+
+
+def _grads_of(N, tparams, graph, batch, decay_c=0., clip_c=-1.):
+    g = graph.mean()
+    g.decay_c, g.clip_c = decay_c, clip_c
+    cost = g.grad_step(*batch, after_grads=lambda: None)
+    return cost, tparams.view_of(g.grads[:tparams.total]), g
+
+
+def _relerr(a, b):
+    return np.linalg.norm(a.astype('float64') - b) / max(np.linalg.norm(b), 1e-30)
+
+
+CASES = [
+    dict(D=8, W=6, A=5, V=50, B=3, max_x=8, max_y=5),          # golden dims (bulk-copy path, C % 4 == 0)
+    dict(D=7, W=5, A=3, V=40, B=2, max_x=9, max_y=4),          # odd sizes: scalar / non-bulk fallbacks
+    dict(D=64, W=20, A=12, V=300, B=5, max_x=37, max_y=11),    # toy-config dims (BASELINE config 1)
+    dict(D=40, W=16, A=33, V=200, B=35, max_x=21, max_y=9),    # batch > 32: second row tile of the step GEMMs
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_cost_and_grads_match_oracle(N, case):
+    opts = toy_options(D=case['D'], W=case['W'], A=case['A'], V=case['V'])
+    P = toy_params(opts)
+    batch = ragged_batch(case['V'], B=case['B'], max_x=case['max_x'], max_y=case['max_y'], seed=11)
+    tparams, graph = _setup(N, opts, P)
+    cost_ref, cache = O.model_fwd(P, *batch)
+    cost = graph.f_log_probs(*batch)
+    np.testing.assert_allclose(cost, cost_ref, rtol=1e-4)
+    mean_ref, G, _ = O.f_grad(P, *batch)
+    mean_cost, Gd, _ = _grads_of(N, tparams, graph, batch)
+    assert abs(mean_cost - mean_ref) <= 1e-4 * abs(mean_ref)
+    for k in G:
+        if np.linalg.norm(G[k]) < 1e-12:
+            assert np.abs(Gd[k]).max() < 1e-6, k        # decoder_c_att: exact gradient is 0
+        else:
+            assert _relerr(Gd[k], G[k]) <= 1e-3, (k, _relerr(Gd[k], G[k]))
+    # second and third call exercise the CUDA-graph capture + replay of the same shape
+    for _ in range(3):
+        c2, Gd2, _ = _grads_of(N, tparams, graph, batch)
+        assert abs(c2 - mean_ref) <= 1e-4 * abs(mean_ref)
+    for k in G:
+        if np.linalg.norm(G[k]) >= 1e-12:
+            assert _relerr(Gd2[k], G[k]) <= 1e-3, k
+
+
+def test_golden_train_fixture(N):
+    z = np.load(os.path.join(GOLD, 'train_toy.npz'))
+    V, W, D, A = [int(v) for v in z['opt_dims']]
+    opts = toy_options(D=D, W=W, A=A, V=V)
+    names = list(O.init_params(opts).keys())
+    P = O.OrderedDict((k, z['p_' + k]) for k in names)
+    tparams, graph = _setup(N, opts, P)
+    batch = (z['x'], z['x_mask'], z['y'], z['y_mask'])
+    np.testing.assert_allclose(graph.f_log_probs(*batch), z['cost'], rtol=1e-4)
+    _, Gd, _ = _grads_of(N, tparams, graph, batch)
+    for k in names:
+        g = z['g_' + k]
+        if np.linalg.norm(g) >= 1e-12:
+            assert _relerr(Gd[k], g) <= 1e-3, k
+    # one Adadelta step with clipping (nats.py:1145-1173, 1344-1353)
+    tparams2, graph2 = _setup(N, opts, P)
+    gm = graph2.mean()
+    gm.clip_c = 1.0
+    f_grad_shared, f_update = N.adadelta('lr', tparams2, gm, None, gm)
+    f_grad_shared(*batch)
+    f_update(0.01)
+    za = np.load(os.path.join(GOLD, 'adadelta_toy.npz'))
+    new = N.unzip(tparams2)
+    for k in names:
+        np.testing.assert_allclose(new[k], za['p_' + k], rtol=2e-4, atol=2e-6, err_msg=k)
+
+
+def test_workspace_views_match_oracle(N):
+    import ctypes
+    import torch
+    from nats_b200 import _lib
+    opts = toy_options(D=16, W=10, A=9, V=80)
+    P = toy_params(opts)
+    batch = ragged_batch(80, B=4, max_x=13, max_y=7, seed=3)
+    tparams, graph = _setup(N, opts, P)
+    _, cache = O.model_fwd(P, *batch)
+    graph.f_log_probs(*batch)
+    Tx, Ty, B = batch[0].shape[0], batch[2].shape[0], batch[0].shape[1]
+    p = graph.plan(Tx, Ty, B)
+    lib = _lib.load()
+    D, C = 16, 32
+
+    def view(name, shape):
+        ptr = lib.nats_train_ws_view(ctypes.byref(graph.dims), Tx, Ty, B, ctypes.c_void_p(p.ws.data_ptr()),
+                                     name.encode())
+        assert ptr
+        off = (ptr - p.ws.data_ptr()) // 4
+        n = int(np.prod(shape))
+        return p.ws.view(torch.float32)[off:off + n].cpu().numpy().reshape(shape)
+
+    np.testing.assert_allclose(view('ctx', (Tx, B, C)), cache['ctx'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(view('init_state', (B, D)), cache['init_state'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(view('dec_h', (Ty, B, D)), cache['Hs'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(view('dec_ctx', (Ty, B, C)), cache['Cs'], rtol=1e-4, atol=1e-6)
+    al = view('dec_alpha', (Ty, B, Tx))
+    np.testing.assert_allclose(al, cache['As'], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(al.sum(2), 1.0, rtol=1e-5)                     # rows sum to one (nats.py:540)
+    assert np.all(al * (1 - batch[1].T[None]) == 0)                           # zero on padding (nats.py:538-539)
+
+
+@pytest.mark.parametrize('opt', ['adadelta', 'adam', 'rmsprop'])
+def test_optimizers_three_steps(N, opt):
+    opts = toy_options(D=12, W=8, A=6, V=60)
+    P = toy_params(opts)
+    batch = ragged_batch(60, B=4, max_x=10, max_y=6, seed=5)
+    tparams, graph = _setup(N, opts, P)
+    g = graph.mean()
+    g.clip_c, g.decay_c = 5.0, 1e-3
+    f_grad_shared, f_update = getattr(N, opt)('lr', tparams, g, None, g)
+    Pr = O.cast_params(P, 'float64')
+    ref = {'adadelta': O.Adadelta, 'adam': O.Adam, 'rmsprop': O.RMSprop}[opt](Pr)
+    for _ in range(3):
+        cost = f_grad_shared(*batch)
+        f_update(0.01)
+        cr, Gr, _ = O.f_grad(Pr, *batch, decay_c=1e-3, clip_c=5.0)
+        assert abs(cost - cr) <= 2e-4 * abs(cr)
+        ref.grad_shared(Gr)
+        ref.update(Pr)
+    new = N.unzip(tparams)
+    for k in Pr:
+        np.testing.assert_allclose(new[k], Pr[k], rtol=5e-3, atol=2e-5, err_msg=k)
+
+
+def test_sampler_matches_oracle_and_golden(N):
+    z = np.load(os.path.join(GOLD, 'sampler_toy.npz'))
+    zt = np.load(os.path.join(GOLD, 'train_toy.npz'))
+    V, W, D, A = [int(v) for v in zt['opt_dims']]
+    opts = toy_options(D=D, W=W, A=A, V=V)
+    names = list(O.init_params(opts).keys())
+    P = O.OrderedDict((k, zt['p_' + k]) for k in names)
+    tparams = N.init_tparams(O.cast_params(P, 'float32'))
+    f_init, f_next = N.build_sampler(tparams, opts)
+    init_state, ctx = f_init(z['x'])
+    np.testing.assert_allclose(init_state, z['init_state'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(np.asarray(ctx), z['ctx'], rtol=1e-4, atol=1e-6)
+    state = init_state
+    ac = np.zeros((1, ctx.shape[2]), 'float32'); aa = np.zeros((1, ctx.shape[0]), 'float32')
+    for t in range(5):
+        # alternate between the device-resident context handle and a plain ndarray (re-upload + pctx recompute)
+        c_in = ctx if t % 2 == 0 else np.array(ctx)
+        probs, smp, state, alT, c, ac, aa = f_next(z['yprev%d' % t], c_in, state, ac, aa)
+        assert np.abs(probs - z['probs%d' % t]).max() <= 1e-5
+        np.testing.assert_allclose(state, z['state%d' % t], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(alT, z['alpha%d' % t], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(c, z['ctxs%d' % t], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(ac, z['acc_ctx%d' % t], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(aa, z['acc_alpha%d' % t], rtol=1e-4, atol=1e-7)
+        assert 0 <= int(smp[0]) < V
+
+
+def test_sampler_batched_hypotheses(N):
+    """n > 1 hypotheses sharing one source (tile of nats.py:958) == the oracle on the materialised tile."""
+    opts = toy_options(D=16, W=10, A=9, V=80)
+    P = toy_params(opts)
+    P32 = O.cast_params(P, 'float32')
+    tparams = N.init_tparams(P32)
+    f_init, f_next = N.build_sampler(tparams, opts)
+    x = np.array([5, 9, 33, 7, 12, 41, 3, 8, 0], 'int64')[:, None]
+    s0, ctx0 = f_init(x)
+    n = 4
+    rng = np.random.RandomState(0)
+    y = np.array([4, -1, 7, 19], 'int64')
+    state = np.tile(s0, [n, 1]) + 0.1 * rng.randn(n, 16).astype('float32')
+    ac = 0.2 * rng.randn(n, 32).astype('float32')
+    aa = np.abs(0.3 * rng.randn(n, x.shape[0])).astype('float32')
+    ctx_t = np.tile(ctx0, [n, 1])
+    out = f_next(y, ctx_t, state, ac, aa)
+    ref = O.f_next(P, y, np.asarray(ctx_t, 'float64'), state.astype('float64'), ac.astype('float64'),
+                   aa.astype('float64'))
+    for i in (0, 2, 3, 4, 5, 6):
+        np.testing.assert_allclose(out[i], ref[i], rtol=2e-4, atol=2e-6)
+
+
+def test_distraction_scores_match_scipy(N):
+    import scipy.spatial.distance
+    import scipy.stats
+    eng = N.get_engine()
+    k, L, Tx, C, D = 3, 6, 37, 24, 12
+    rng = np.random.RandomState(2)
+    sc = N.DistractionScorer(eng, k, L, Tx, C, D)
+    hist = []
+    for s in range(4):
+        a = rng.rand(k, Tx).astype('float32'); a /= a.sum(1, keepdims=True)
+        c = rng.randn(k, C).astype('float32'); h = rng.randn(k, D).astype('float32')
+        hist.append((a, c, h))
+        sc.advance(a, c, h, [0, 1, 2])
+    a = rng.rand(k, Tx).astype('float32'); a /= a.sum(1, keepdims=True)
+    c = rng.randn(k, C).astype('float32'); h = rng.randn(k, D).astype('float32')
+    pen = sc.penalties(a, c, h, k, 1.5, 0.7, 2.0)
+    for i in range(k):
+        kl = min(scipy.stats.entropy(hh[0][i], a[i]) for hh in hist)
+        cc = max(scipy.spatial.distance.cosine(hh[1][i], c[i]) for hh in hist)
+        ss = max(scipy.spatial.distance.cosine(hh[2][i], h[i]) for hh in hist)
+        np.testing.assert_allclose(pen[:, i], [-1.5 * kl, 0.7 * cc, 2.0 * ss], rtol=2e-4, atol=2e-6)
+    # reorder: new hypothesis 0 descends from old 2, new 1 from old 0
+    sc.advance(a, c, h, [2, 0])
+    pen2 = sc.penalties(a[[2, 0]], c[[2, 0]], h[[2, 0]], 2, 1.0, 1.0, 1.0)
+    # the newest history entry equals the current vectors: min KL = 0; the cosine maxima come from older entries
+    np.testing.assert_allclose(pen2[0], 0.0, atol=1e-5)
+    for j, i in enumerate((2, 0)):
+        cc = max(scipy.spatial.distance.cosine(hh[1][i], c[i]) for hh in hist)
+        ss = max(scipy.spatial.distance.cosine(hh[2][i], h[i]) for hh in hist)
+        np.testing.assert_allclose(pen2[1:, j], [cc, ss], rtol=2e-4, atol=2e-6)
+
+
+def test_beam_search_matches_oracle_and_golden(N):
+    z = np.load(os.path.join(GOLD, 'beam_toy.npz'))
+    zt = np.load(os.path.join(GOLD, 'train_toy.npz'))
+    V, W, D, A = [int(v) for v in zt['opt_dims']]
+    opts = toy_options(D=D, W=W, A=A, V=V)
+    names = list(O.init_params(opts).keys())
+    P32 = O.cast_params(O.OrderedDict((k, zt['p_' + k]) for k in names), 'float32')
+    tparams = N.init_tparams(P32)
+    f_init, f_next = N.build_sampler(tparams, opts)
+    samples, scores, alphas = N.gen_sample(tparams, f_init, f_next, z['x'], opts, k=3, maxlen=7, stochastic=False,
+                                           use_unk=True, kl_factor=1.5, ctx_factor=1.5, state_factor=1.5)
+    assert len(samples) == int(z['n_samples'])
+    for i, s in enumerate(samples):
+        assert list(map(int, s)) == list(map(int, z['sample%d' % i])), (i, s)
+    np.testing.assert_allclose(np.array(scores, 'float32'), z['scores'], rtol=2e-4)
+    assert all(len(a) == len(s) for a, s in zip(alphas, samples))
+    # no distraction: plain beam search equals the oracle's
+    fi = lambda x_: O.f_init(P32, x_)
+    fn = lambda y_, c_, s_, ac_, aa_: O.f_next(P32, y_, c_, s_.astype('float32'), ac_.astype('float32'),
+                                               aa_.astype('float32'))
+    ref_s, ref_sc, _ = O.gen_sample(fi, fn, z['x'], k=4, maxlen=6, stochastic=False, use_unk=False)
+    got_s, got_sc, _ = N.gen_sample(tparams, f_init, f_next, z['x'], opts, k=4, maxlen=6, stochastic=False,
+                                    use_unk=False)
+    assert [list(map(int, s)) for s in got_s] == [list(map(int, s)) for s in ref_s]
+    np.testing.assert_allclose(np.array(got_sc), np.array(ref_sc), rtol=2e-4)
+    # stochastic argmax decoding
+    s1, _, _ = N.gen_sample(tparams, f_init, f_next, z['x'], opts, k=1, maxlen=6, stochastic=True, argmax=True)
+    s2, _, _ = O.gen_sample(fi, fn, z['x'], k=1, maxlen=6, stochastic=True, argmax=True)
+    assert list(map(int, s1)) == list(map(int, s2))
+
+
+def test_full_size_properties(N):
+    """BASELINE config 2 shape (Tx=120, Ty=20, D=500, V=4000, B=64 -> here B=16 to keep the oracle out): size-
+    independent properties only: alpha rows sum to 1, acc_alpha row sums = #valid steps, padding invariance of the
+    cost, cost finite and ~ Ty*log(V) at init."""
+    opts = dict(dim_word=100, dim=500, dim_att=100, n_words=4000, encoder='gru', decoder='gru_cond')
+    np.random.seed(1234)
+    P = N.init_params(opts)
+    tparams = N.init_tparams(P)
+    graph = N.build_model(tparams, opts)[-1]
+    x, xm, y, ym = full_batch(4000, B=16, Tx=120, Ty=20)
+    cost = graph.f_log_probs(x, xm, y, ym)
+    assert np.all(np.isfinite(cost))
+    np.testing.assert_allclose(cost, 20 * np.log(4000.), rtol=0.02)
+    pad = lambda a, n: np.concatenate([a, np.zeros((n,) + a.shape[1:], a.dtype)], 0)
+    cost2 = graph.f_log_probs(pad(x, 5), pad(xm, 5), pad(y, 3), pad(ym, 3))
+    np.testing.assert_allclose(cost2, cost, rtol=1e-5)
+    g = graph.mean()
+    c1 = g.grad_step(x, xm, y, ym, after_grads=lambda: None)
+    assert np.isfinite(c1) and abs(c1 - cost.mean()) < 1e-3 * cost.mean()
+    gn = float(g.grads[:tparams.total].double().pow(2).sum().sqrt().item())
+    assert np.isfinite(gn) and gn > 0
