@@ -335,12 +335,26 @@ inline size_t context_smem(int Tx, bool bulk, int slice_pad) {
 
 }  // namespace
 
+template <class K>
+static int set_max_dyn_smem(K kernel, int optin, int* out_limit) {
+    cudaFuncAttributes fa;
+    NATS_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
+    const int lim = optin - (int)fa.sharedSizeBytes;      // dynamic + static must fit the opt-in limit
+    NATS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    if (out_limit && lim < *out_limit) *out_limit = lim;
+    return 0;
+}
+
+static int g_att_dyn_limit = 0;
+
 int attention_setup(const nats_ctx* ctx) {
-    const int lim = ctx->max_smem_optin;
-    NATS_CUDA_OK(cudaFuncSetAttribute(att_context_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NATS_CUDA_OK(cudaFuncSetAttribute(att_context_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NATS_CUDA_OK(cudaFuncSetAttribute(att_bwd_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NATS_CUDA_OK(cudaFuncSetAttribute(att_bwd_dalpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    int lim = ctx->max_smem_optin;
+    NATS_TRY(set_max_dyn_smem(att_context_kernel<true>, ctx->max_smem_optin, &lim));
+    NATS_TRY(set_max_dyn_smem(att_context_kernel<false>, ctx->max_smem_optin, &lim));
+    NATS_TRY(set_max_dyn_smem(att_bwd_softmax_kernel, ctx->max_smem_optin, &lim));
+    NATS_TRY(set_max_dyn_smem(att_bwd_dalpha_kernel, ctx->max_smem_optin, &lim));
+    NATS_TRY(set_max_dyn_smem(att_scores_kernel, ctx->max_smem_optin, &lim));
+    g_att_dyn_limit = lim;
     return 0;
 }
 
@@ -364,8 +378,8 @@ int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
                          ((reinterpret_cast<uintptr_t>(a.cc) & 15) == 0);
     bool bulk = aligned;
     size_t smem = context_smem(a.Tx, bulk, slice_pad);
-    if (bulk && smem > (size_t)ctx->max_smem_optin) { bulk = false; smem = context_smem(a.Tx, false, slice_pad); }
-    NATS_REQUIRE(smem <= (size_t)ctx->max_smem_optin, "source too long for the attention kernel's shared memory");
+    if (bulk && smem > (size_t)g_att_dyn_limit) { bulk = false; smem = context_smem(a.Tx, false, slice_pad); }
+    NATS_REQUIRE(smem <= (size_t)g_att_dyn_limit, "source too long for the attention kernel's shared memory");
     dim3 grid(nslices, a.n);
     if (bulk) att_context_kernel<true><<<grid, kAttThreads, smem, st>>>(a, slice, slice_pad);
     else att_context_kernel<false><<<grid, kAttThreads, smem, st>>>(a, slice, slice_pad);
@@ -384,7 +398,7 @@ int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a) {
     }
     {
         const size_t smem = ((size_t)2 * a.Tx + 3 * a.A + (size_t)kSoftWarps * 3 * a.A) * sizeof(float);
-        NATS_REQUIRE(smem <= (size_t)ctx->max_smem_optin, "source too long for the attention backward kernel");
+        NATS_REQUIRE(smem <= (size_t)g_att_dyn_limit, "source too long for the attention backward kernel");
         att_bwd_softmax_kernel<<<a.B, kSoftThreads, smem, st>>>(a);
         NATS_LAUNCH_OK();
     }
