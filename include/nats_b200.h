@@ -170,6 +170,15 @@ int nats_beam_distraction_scores(nats_ctx_t* ctx, void* stream,
 int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, float* dst, const float* cur,
                              const int32_t* parent, int n_new, int len_cap, int hist_len, int dim);
 
+/* ---------------------------------------------------------------- diagnostics ------------------- */
+/* Per-kernel-class timing with CUDA events on the launch stream (eager launches only; keep it off while a step
+ * is captured into a CUDA graph).  nats_profile_read synchronises the device and returns, per class, the summed
+ * milliseconds, algorithmic flops / bytes declared at the launch sites, and the number of launches. */
+int nats_profile_enable(nats_ctx_t* ctx, int on);
+int nats_profile_num_classes(void);
+const char* nats_profile_class_name(int cls);
+int nats_profile_read(nats_ctx_t* ctx, int n_classes, double* ms, double* flops, double* bytes, int64_t* launches);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus

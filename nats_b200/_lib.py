@@ -2,7 +2,7 @@
 missing or fails to load, importing the product path raises."""
 import ctypes
 import os
-from ctypes import (POINTER, Structure, c_char, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64,
+from ctypes import (POINTER, Structure, c_char, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64,
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -58,6 +58,11 @@ SIGNATURES = {
     'nats_beam_distraction_scores': (c_int, [c_void_p, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                              _P, _P, _P, c_float, c_float, c_float, _P, _P]),
     'nats_beam_reorder_append': (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int]),
+    'nats_profile_enable': (c_int, [c_void_p, c_int]),
+    'nats_profile_num_classes': (c_int, []),
+    'nats_profile_class_name': (c_char_p, [c_int]),
+    'nats_profile_read': (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_double),
+                                  POINTER(c_int64)]),
 }
 
 _lib = None

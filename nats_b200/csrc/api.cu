@@ -1,6 +1,8 @@
 // api.cu -- the C ABI of libnats_b200.so (declared in include/nats_b200.h).
 #include <stdarg.h>
 
+#include <vector>
+
 #include "model.cuh"
 
 namespace nats {
@@ -10,6 +12,41 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+}  // namespace nats
+
+// ------------------------------------------------------------------ per-kernel-class profiler (prof.cuh)
+namespace nats {
+namespace {
+struct ProfRec { int cls; double flops, bytes; };
+struct ProfState {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;     // pairs: 2*i = start, 2*i+1 = stop
+    std::vector<ProfRec> recs;
+};
+ProfState g_prof;
+const char* kNames[K_COUNT] = {
+    "gemm_big_nn", "gemm_big_nt", "gemm_big_tn", "gemm_big_tt", "gemm_mid_nn", "gemm_mid_nt", "gemm_mid_tn",
+    "gemm_mid_tt", "gemm_smallm_nn", "gemm_smallm_nt", "gemm_smallm_tn", "gemm_smallm_tt", "gru_gates_fwd",
+    "gru_gates_bwd", "att_scores", "att_context", "att_bwd_ctx", "att_bwd_dalpha", "att_bwd_softmax", "nll_rows",
+    "dlogits", "softmax_sample", "colsum", "reduce_splits", "embedding", "elementwise", "optimizer", "beam",
+    "memset"};
+}  // namespace
+const char* kclass_name(int cls) { return (cls >= 0 && cls < K_COUNT) ? kNames[cls] : "?"; }
+bool prof_enabled() { return g_prof.on; }
+void prof_begin(cudaStream_t st, int cls, double flops, double bytes) {
+    const size_t i = g_prof.recs.size();
+    while (g_prof.ev.size() < 2 * (i + 1)) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { g_prof.on = false; return; }
+        g_prof.ev.push_back(e);
+    }
+    g_prof.recs.push_back(ProfRec{cls, flops, bytes});
+    cudaEventRecord(g_prof.ev[2 * i], st);
+}
+void prof_end(cudaStream_t st) {
+    if (g_prof.recs.empty()) return;
+    cudaEventRecord(g_prof.ev[2 * (g_prof.recs.size() - 1) + 1], st);
 }
 }  // namespace nats
 
@@ -123,6 +160,30 @@ int nats_param_layout(const nats_dims_t* dims, nats_param_view_t* views, int64_t
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ profiling
+int nats_profile_enable(nats_ctx_t* ctx, int on) {
+    (void)ctx;
+    g_prof.recs.clear();
+    g_prof.on = on != 0;
+    return 0;
+}
+int nats_profile_num_classes(void) { return K_COUNT; }
+const char* nats_profile_class_name(int cls) { return kclass_name(cls); }
+int nats_profile_read(nats_ctx_t* ctx, int n_classes, double* ms, double* flops, double* bytes, int64_t* launches) {
+    (void)ctx;
+    NATS_REQUIRE(n_classes >= K_COUNT && ms && flops && bytes && launches, "profile_read buffers");
+    NATS_CUDA_OK(cudaDeviceSynchronize());
+    for (int i = 0; i < n_classes; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+    for (size_t i = 0; i < g_prof.recs.size(); ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) != cudaSuccess) continue;
+        const ProfRec& r = g_prof.recs[i];
+        ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
+    }
+    g_prof.recs.clear();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ training
 int64_t nats_train_workspace_bytes(const nats_dims_t* dims, int Tx, int Ty, int B) {
     if (check_dims(dims) != 0 || Tx < 1 || Ty < 1 || B < 1) return -1;
@@ -196,7 +257,7 @@ int nats_train_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const
     NATS_TRAIN_PROLOGUE();
     NATS_REQUIRE(x && x_mask && y && y_mask && grads && params, "null argument");
     const ParamOff o = param_offsets(*dims);
-    NATS_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)(o.total + NATS_GRAD_TAIL) * sizeof(float), st));
+    NATS_CUDA_OK(memset_async(st, grads, 0, (size_t)(o.total + NATS_GRAD_TAIL) * sizeof(float)));
     NATS_TRY(cost_reduce(st, w.rowcost, Ty, B, nullptr, scale, grads + o.total));
     NATS_TRY(train_readout_bwd(ctx, st, *dims, params, y, y_mask, Ty, B, w, scale, grads));
     NATS_TRY(train_decoder_bwd(ctx, st, *dims, params, y, x_mask, y_mask, Tx, Ty, B, w, grads));

@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "../../include/nats_b200.h"
+#include "prof.cuh"
 
 namespace nats {
 

@@ -222,6 +222,15 @@ int launch_cfg(cudaStream_t st, const GemmGroup& grp, bool ta, bool tb) {
     const int gz = grp.zstart[grp.count];
     if (gx == 0 || gy == 0 || gz == 0) return 0;
     dim3 grid(gx, gy, gz), block((BM / TM) * (BN / TN));
+    double flops = 0.0, bytes = 0.0;
+    if (prof_enabled())
+        for (int i = 0; i < grp.count; ++i) {
+            const GemmProblem& q = grp.p[i];
+            flops += 2.0 * q.M * q.N * q.K * q.batch;
+            bytes += 4.0 * q.batch * ((double)q.M * q.K + (double)q.K * q.N + (double)q.M * q.N * q.splitk);
+        }
+    const int cfg_id = (BM == 128) ? 0 : (BM == 64 ? 1 : 2);
+    ProfScope ps(st, K_GEMM_BASE + cfg_id * 4 + (ta ? 2 : 0) + (tb ? 1 : 0), flops, bytes);
     if (!ta && !tb) sgemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, block, 0, st>>>(grp);
     else if (!ta && tb) sgemm_kernel<BM, BN, BK, TM, TN, false, true><<<grid, block, 0, st>>>(grp);
     else if (ta && !tb) sgemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, block, 0, st>>>(grp);
@@ -301,6 +310,7 @@ int reduce_splits(cudaStream_t st, const float* part, int nsplit, long long stri
     long long gl = (total + block - 1) / block;
     if (gl > 148LL * 16) gl = 148LL * 16;
     const int grid = (int)gl;
+    ProfScope ps(st, K_REDUCE_SPLITS, 0.0, 4.0 * total * (nsplit + 1));
     reduce_splits_kernel<<<grid, block, 0, st>>>(part, nsplit, strideP, M, N, ldp, out, ldo, bias, accumulate);
     NATS_LAUNCH_OK();
     return 0;

@@ -55,10 +55,10 @@ int train_decoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
     const int S4 = gemm_pick_split(ctx, B, D, D3);    // d h_   <- dG2 . Ucat^T       (slabs in part_c)
     const long long spD = (long long)B * D, spC = (long long)B * C;
 
-    NATS_CUDA_OK(cudaMemsetAsync(w.dpctx, 0, (size_t)XB * A * sizeof(float), st));
-    NATS_CUDA_OK(cudaMemsetAsync(w.dacc_alpha, 0, (size_t)B * Tx * sizeof(float), st));
-    NATS_CUDA_OK(cudaMemsetAsync(w.dacc_ctx, 0, (size_t)2 * B * C * sizeof(float), st));
-    NATS_CUDA_OK(cudaMemsetAsync(w.gatt_part, 0, (size_t)B * (2 * A + 1) * sizeof(float), st));
+    NATS_CUDA_OK(memset_async(st, w.dpctx, 0, (size_t)XB * A * sizeof(float)));
+    NATS_CUDA_OK(memset_async(st, w.dacc_alpha, 0, (size_t)B * Tx * sizeof(float)));
+    NATS_CUDA_OK(memset_async(st, w.dacc_ctx, 0, (size_t)2 * B * C * sizeof(float)));
+    NATS_CUDA_OK(memset_async(st, w.gatt_part, 0, (size_t)B * (2 * A + 1) * sizeof(float)));
 
     for (int t = Ty - 1; t >= 0; --t) {
         const long long rD = (long long)t * B * D, rC = (long long)t * B * C, rT = (long long)t * B * Tx;

@@ -23,7 +23,7 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
         }
         NATS_TRY(gemm_launch(st, pr, 2, false, false, GEMM_CFG_AUTO));
     }
-    NATS_CUDA_OK(cudaMemsetAsync(e.ctxsum, 0, (size_t)n * C * sizeof(float), st));
+    NATS_CUDA_OK(memset_async(st, e.ctxsum, 0, (size_t)n * C * sizeof(float)));
     const int S = gemm_pick_split(ctx, n, D3, D);
     const int cfg = gemm_step_cfg(n);
     const long long strideP = 2LL * n * D3;
@@ -176,8 +176,8 @@ int train_decoder_fwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
         p.bias = params + o.b_att;
         NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
     }
-    NATS_CUDA_OK(cudaMemsetAsync(w.d_accalpha, 0, (size_t)B * Tx * sizeof(float), st));   // nats.py:599-603
-    NATS_CUDA_OK(cudaMemsetAsync(w.d_accctx, 0, (size_t)B * C * sizeof(float), st));
+    NATS_CUDA_OK(memset_async(st, w.d_accalpha, 0, (size_t)B * Tx * sizeof(float)));   // nats.py:599-603
+    NATS_CUDA_OK(memset_async(st, w.d_accctx, 0, (size_t)B * C * sizeof(float)));
     for (int t = 0; t < Ty; ++t) {
         const long long rD = (long long)t * B * D, rC = (long long)t * B * C, rT = (long long)t * B * Tx;
         DecStep s;

@@ -362,6 +362,7 @@ int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
     NATS_REQUIRE(a.Tx >= 1 && a.n >= 1, "attention shape");
     {
         dim3 grid(cdiv(a.Tx, kRowsPerCta), a.n);
+        ProfScope ps(st, K_ATT_SCORES, 0.0, 4.0 * a.Tx * (a.pctx_bstride == 0 ? 1 : a.n) * a.A);
         att_scores_kernel<<<grid, kAttThreads, 3 * a.A * sizeof(float), st>>>(a);
         NATS_LAUNCH_OK();
     }
@@ -381,6 +382,8 @@ int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
     if (bulk && smem > (size_t)g_att_dyn_limit) { bulk = false; smem = context_smem(a.Tx, false, slice_pad); }
     NATS_REQUIRE(smem <= (size_t)g_att_dyn_limit, "source too long for the attention kernel's shared memory");
     dim3 grid(nslices, a.n);
+    ProfScope ps(st, K_ATT_CONTEXT, 2.0 * a.Tx * a.n * a.C,
+                 4.0 * ((double)a.Tx * (a.cc_bstride == 0 ? 1 : a.n) * a.C + 3.0 * a.n * a.Tx + 4.0 * a.n * a.C));
     if (bulk) att_context_kernel<true><<<grid, kAttThreads, smem, st>>>(a, slice, slice_pad);
     else att_context_kernel<false><<<grid, kAttThreads, smem, st>>>(a, slice, slice_pad);
     NATS_LAUNCH_OK();
@@ -389,16 +392,21 @@ int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
 
 int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a) {
     NATS_REQUIRE(a.A <= 32 * kMaxAk, "dim_att > 256 not supported by the attention backward kernel");
-    att_bwd_ctx_kernel<<<cdiv(a.B * a.C, 256), 256, 0, st>>>(a);
-    NATS_LAUNCH_OK();
+    {
+        ProfScope ps(st, K_ATT_BWD_CTX);
+        att_bwd_ctx_kernel<<<cdiv(a.B * a.C, 256), 256, 0, st>>>(a);
+        NATS_LAUNCH_OK();
+    }
     {
         dim3 grid(cdiv(a.Tx, kRowsPerCta), a.B);
+        ProfScope ps(st, K_ATT_BWD_DALPHA, 2.0 * a.Tx * a.B * a.C, 4.0 * ((double)a.Tx * a.B * a.C + 2.0 * a.B * a.Tx));
         att_bwd_dalpha_kernel<<<grid, kAttThreads, (size_t)a.C * sizeof(float), st>>>(a);
         NATS_LAUNCH_OK();
     }
     {
         const size_t smem = ((size_t)2 * a.Tx + 3 * a.A + (size_t)kSoftWarps * 3 * a.A) * sizeof(float);
         NATS_REQUIRE(smem <= (size_t)g_att_dyn_limit, "source too long for the attention backward kernel");
+        ProfScope ps(st, K_ATT_BWD_SOFTMAX, 0.0, 12.0 * a.Tx * a.B * a.A);
         att_bwd_softmax_kernel<<<a.B, kSoftThreads, smem, st>>>(a);
         NATS_LAUNCH_OK();
     }

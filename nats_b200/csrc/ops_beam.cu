@@ -82,6 +82,7 @@ int beam_distraction_scores(cudaStream_t st, const float* hist_alpha, const floa
                             float* out) {
     NATS_REQUIRE(hist_len >= 1 && live_k >= 1 && hist_len <= len_cap, "beam history shape");
     dim3 grid(hist_len, live_k);
+    ProfScope ps(st, K_BEAM);
     beam_pair_kernel<<<grid, 256, 0, st>>>(hist_alpha, hist_ctx, hist_state, len_cap, hist_len, Tx, C, D, cur_alpha,
                                            cur_ctx, cur_state, scratch);
     NATS_LAUNCH_OK();
@@ -94,6 +95,7 @@ int beam_reorder_append(cudaStream_t st, const float* src, float* dst, const flo
                         int n_new, int len_cap, int hist_len, int dim) {
     NATS_REQUIRE(n_new >= 1 && hist_len < len_cap, "beam reorder shape");
     dim3 grid(n_new, hist_len + 1);
+    ProfScope ps(st, K_BEAM);
     beam_reorder_kernel<<<grid, 256, 0, st>>>(src, dst, cur, parent, len_cap, hist_len, dim);
     NATS_LAUNCH_OK();
     return 0;

@@ -203,6 +203,7 @@ int gather_rows(cudaStream_t st, const float* Wemb, const int64_t* ids, int n_ro
                 float* out) {
     const long long total = (long long)n_rows * W;
     if (total == 0) return 0;
+    ProfScope ps(st, K_EMBED, 0.0, 8.0 * total);
     gather_rows_kernel<<<grid_for(total, 256), 256, 0, st>>>(Wemb, ids, n_rows, W, V, shift, out);
     NATS_LAUNCH_OK();
     return 0;
@@ -211,6 +212,7 @@ int scatter_add_rows(cudaStream_t st, float* dWemb, const int64_t* ids, int n_ro
                      const float* src) {
     const long long total = (long long)n_rows * W;
     if (total == 0) return 0;
+    ProfScope ps(st, K_EMBED, 0.0, 12.0 * total);
     scatter_add_rows_kernel<<<grid_for(total, 256), 256, 0, st>>>(dWemb, ids, n_rows, W, V, shift, src);
     NATS_LAUNCH_OK();
     return 0;
@@ -222,6 +224,7 @@ int gru_gates_fwd(cudaStream_t st, const GateFwd* groups, int ngroups, int B, in
     memset(&pack, 0, sizeof(pack));
     for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
     dim3 grid(cdiv(B * D, 256), ngroups);
+    ProfScope ps(st, K_GATES_FWD);
     if (mode == 0) gru_gates_fwd_kernel<0><<<grid, 256, 0, st>>>(pack, B, D);
     else gru_gates_fwd_kernel<1><<<grid, 256, 0, st>>>(pack, B, D);
     NATS_LAUNCH_OK();
@@ -233,6 +236,7 @@ int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, in
     memset(&pack, 0, sizeof(pack));
     for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
     dim3 grid(cdiv(B * D, 256), ngroups);
+    ProfScope ps(st, K_GATES_BWD);
     gru_gates_bwd_kernel<<<grid, 256, 0, st>>>(pack, B, D);
     NATS_LAUNCH_OK();
     return 0;
@@ -240,12 +244,14 @@ int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, in
 
 int tanh_inplace(cudaStream_t st, float* x, long long n) {
     if (n == 0) return 0;
+    ProfScope ps(st, K_ELEMWISE);
     tanh_inplace_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, n);
     NATS_LAUNCH_OK();
     return 0;
 }
 int dtanh(cudaStream_t st, const float* g, const float* y, float* dst, long long n) {
     if (n == 0) return 0;
+    ProfScope ps(st, K_ELEMWISE);
     dtanh_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, y, dst, n);
     NATS_LAUNCH_OK();
     return 0;
@@ -253,16 +259,19 @@ int dtanh(cudaStream_t st, const float* g, const float* y, float* dst, long long
 int sum_parts_dtanh(cudaStream_t st, const float* a, const float* part, int nsplit, long long part_stride,
                     const float* y, float* dst, int B, int D) {
     const int n = B * D;
+    ProfScope ps(st, K_ELEMWISE);
     sum_parts_dtanh_kernel<<<cdiv(n, 256), 256, 0, st>>>(a, part, nsplit, part_stride, y, dst, n);
     NATS_LAUNCH_OK();
     return 0;
 }
 int mask_lengths(cudaStream_t st, const float* mask, int Tx, int B, float* xlen, float* inv) {
+    ProfScope ps(st, K_ELEMWISE);
     mask_lengths_kernel<<<cdiv(B, 128), 128, 0, st>>>(mask, Tx, B, xlen, inv);
     NATS_LAUNCH_OK();
     return 0;
 }
 int scale_rows(cudaStream_t st, const float* src, const float* inv, int B, int C, float* out) {
+    ProfScope ps(st, K_ELEMWISE);
     scale_rows_kernel<<<cdiv(B * C, 256), 256, 0, st>>>(src, inv, B, C, out);
     NATS_LAUNCH_OK();
     return 0;
@@ -276,6 +285,7 @@ static int colsum_impl(cudaStream_t st, const float* X, const float* Y, long lon
     if (ks < 1) ks = 1;
     const long long rows_per = (K + ks - 1) / ks;
     dim3 grid(cdiv(N, 32), ks), block(32, 8);
+    ProfScope ps(st, K_COLSUM, 0.0, 4.0 * (double)K * N * (Y ? 2 : 1));
     if (Y) colsum_stage1<true><<<grid, block, 0, st>>>(X, Y, K, N, ld, rows_per, scratch);
     else colsum_stage1<false><<<grid, block, 0, st>>>(X, nullptr, K, N, ld, rows_per, scratch);
     NATS_LAUNCH_OK();
@@ -291,6 +301,7 @@ int colsum_prod(cudaStream_t st, const float* X, const float* Y, long long K, in
     return colsum_impl(st, X, Y, K, N, ld, out, accumulate, scratch);
 }
 int cost_reduce(cudaStream_t st, const float* rowcost, int Ty, int B, float* cost, float scale, float* total) {
+    ProfScope ps(st, K_ELEMWISE);
     cost_reduce_kernel<<<1, 256, 0, st>>>(rowcost, Ty, B, cost, scale, total);
     NATS_LAUNCH_OK();
     return 0;

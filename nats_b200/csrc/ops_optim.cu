@@ -94,6 +94,7 @@ int grad_clip(const nats_ctx* ctx, cudaStream_t st, long long n, const float* pa
               float clip_c, float* stats) {
     if (n == 0) return 0;
     float* part = ctx->dev_scratch;
+    ProfScope ps(st, K_OPTIM, 0.0, 4.0 * n * ((clip_c > 0.f ? 3 : 1) + (decay_c > 0.f ? 4 : 0)));
     if (decay_c > 0.f) {
         sumsq_stage1<<<kRedBlocks, 256, 0, st>>>(params, n, part);
         NATS_LAUNCH_OK();
@@ -114,6 +115,7 @@ int grad_clip(const nats_ctx* ctx, cudaStream_t st, long long n, const float* pa
 }
 int adadelta_grad_shared(cudaStream_t st, long long n, const float* zg, float* rg2, float rho) {
     if (n == 0) return 0;
+    ProfScope ps(st, K_OPTIM, 0.0, 12.0 * n);
     adadelta_gs_kernel<<<flat_grid(n), 256, 0, st>>>(zg, rg2, n, rho);
     NATS_LAUNCH_OK();
     return 0;
@@ -121,6 +123,7 @@ int adadelta_grad_shared(cudaStream_t st, long long n, const float* zg, float* r
 int adadelta_update(cudaStream_t st, long long n, float* p, const float* zg, float* ru2, const float* rg2, float rho,
                     float eps) {
     if (n == 0) return 0;
+    ProfScope ps(st, K_OPTIM, 0.0, 24.0 * n);
     adadelta_up_kernel<<<flat_grid(n), 256, 0, st>>>(p, zg, ru2, rg2, n, rho, eps);
     NATS_LAUNCH_OK();
     return 0;
@@ -131,12 +134,14 @@ int adam_update(cudaStream_t st, long long n, float* p, const float* g, float* m
     const float i_t = (float)step + 1.f;
     const float fix1 = 1.f - powf(b1, i_t), fix2 = 1.f - powf(b2, i_t);
     const float lr_t = lr0 * (sqrtf(fix2) / fix1);                     // nats.py:1123-1125
+    ProfScope ps(st, K_OPTIM, 0.0, 28.0 * n);
     adam_kernel<<<flat_grid(n), 256, 0, st>>>(p, g, m, v, n, b1, b2, e, lr_t);
     NATS_LAUNCH_OK();
     return 0;
 }
 int rmsprop_grad_shared(cudaStream_t st, long long n, const float* zg, float* rg, float* rg2) {
     if (n == 0) return 0;
+    ProfScope ps(st, K_OPTIM, 0.0, 20.0 * n);
     rmsprop_gs_kernel<<<flat_grid(n), 256, 0, st>>>(zg, rg, rg2, n);
     NATS_LAUNCH_OK();
     return 0;
@@ -144,6 +149,7 @@ int rmsprop_grad_shared(cudaStream_t st, long long n, const float* zg, float* rg
 int rmsprop_update(cudaStream_t st, long long n, float* p, const float* zg, float* ud, const float* rg,
                    const float* rg2) {
     if (n == 0) return 0;
+    ProfScope ps(st, K_OPTIM, 0.0, 28.0 * n);
     rmsprop_up_kernel<<<flat_grid(n), 256, 0, st>>>(p, zg, ud, rg, rg2, n);
     NATS_LAUNCH_OK();
     return 0;

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kRowThreads) softmax_sample_kernel(const float
 int nll_rows(cudaStream_t st, const float* logits, int rows, int V, const int64_t* y, const float* ymask, float* lse,
              float* rowcost) {
     if (rows == 0) return 0;
+    ProfScope ps(st, K_NLL, 0.0, 8.0 * rows * V);
     nll_rows_kernel<<<rows, kRowThreads, 0, st>>>(logits, V, y, ymask, lse, rowcost);
     NATS_LAUNCH_OK();
     return 0;
@@ -121,6 +122,7 @@ int dlogits_inplace(cudaStream_t st, float* logits, int rows, int V, const int64
     int gx = cdiv(V, 256 * 4);
     if (gx < 1) gx = 1;
     dim3 grid(gx, rows);
+    ProfScope ps(st, K_DLOGITS, 0.0, 8.0 * rows * V);
     dlogits_kernel<<<grid, 256, 0, st>>>(logits, rows, V, y, ymask, lse, scale);
     NATS_LAUNCH_OK();
     return 0;
@@ -128,6 +130,7 @@ int dlogits_inplace(cudaStream_t st, float* logits, int rows, int V, const int64
 int softmax_sample_rows(cudaStream_t st, const float* logits, int rows, int V, float* probs, int64_t* sample,
                         uint64_t seed, uint64_t step) {
     if (rows == 0) return 0;
+    ProfScope ps(st, K_SOFTMAX_SAMPLE, 0.0, 16.0 * rows * V);
     softmax_sample_kernel<<<rows, kRowThreads, 0, st>>>(logits, V, probs, sample, seed, step);
     NATS_LAUNCH_OK();
     return 0;

@@ -547,6 +547,7 @@ def adadelta(lr, tparams, grads, inp, cost, epsilon=1e-6, rho=0.95):
         return []
 
     f_grad_shared.state = dict(running_up2=running_up2, running_grads2=running_grads2)
+    f_grad_shared.accum = accum
     return f_grad_shared, f_update
 
 

@@ -246,7 +246,7 @@ def gru_cond_step(P, m_, x_, xx_, h_, acc_ctx, acc_alpha, pctx_, cc_, context_ma
     if context_mask is not None:
         a = a * context_mask.astype(dt)                                 # :538-539
     alpha = a / a.sum(0, keepdims=True)                                 # :540
-    craw = (cc_ * alpha[:, :, None]).sum(0)                             # :541  [B,C]
+    craw = np.einsum('tb,tbc->bc', alpha, cc_)                          # :541  [B,C] (no [Tx,B,C] temporary)
 
     # distraction over past context vectors (:545-546); U_con, W_con are per-channel scales
     ctx = np.tanh(U_con[:, 0][None, :] * craw + acc_ctx * W_con[:, 0][None, :])
@@ -312,7 +312,8 @@ def gru_cond_layer_bwd(P, cache, dHs, dCs, G, prefix='decoder'):
     ucon, wcon, dwei, uatt = U_con[:, 0], W_con[:, 0], D_wei[0], U_att[:, 0]
 
     dxg = np.zeros((Ty, B, 2 * D), dt); dxx = np.zeros((Ty, B, D), dt)
-    dpctx = np.zeros_like(pctx); dcc = np.zeros_like(cc)
+    dpctx = np.zeros_like(pctx)
+    dcraws = np.zeros((Ty, B, C), dt)
     dh = np.zeros((B, D), dt)
     dacc_ctx = np.zeros((B, C), dt); dacc_alpha = np.zeros((B, Tx), dt)
     for t in range(Ty - 1, -1, -1):
@@ -345,7 +346,7 @@ def gru_cond_layer_bwd(P, cache, dHs, dCs, G, prefix='decoder'):
         # attention backward (:527-541)
         alpha, z = s['alpha'], s['z']                                     # [Tx,B], [Tx,B,A]
         dalpha = np.einsum('tbc,bc->tb', cc, dcraw) + dalphaT.T           # :541
-        dcc += alpha[:, :, None] * dcraw[None, :, :]
+        dcraws[t] = dcraw                                                 # d cc summed after the loop
         de = alpha * (dalpha - (alpha * dalpha).sum(0, keepdims=True))    # :537-540 (masked softmax)
         G[p + '_c_att'][0] += de.sum()
         G[p + '_U_att'][:, 0] += np.einsum('tb,tba->a', de, z)
@@ -378,7 +379,10 @@ def gru_cond_layer_bwd(P, cache, dHs, dCs, G, prefix='decoder'):
     G[p + '_bx'] += dxx.sum((0, 1))
     G[p + '_Wc_att'] += cc.reshape(Tx * B, C).T @ dpctx.reshape(Tx * B, -1)
     G[p + '_b_att'] += dpctx.sum((0, 1))
-    dcc += dpctx @ Wc_att.T
+    alphas = np.stack([s_['alpha'] for s_ in cache['steps']])            # [Ty,Tx,B]
+    # d cc[t,b,:] = sum_s alpha_s[t,b] dcraw_s[b,:]  (one batched product instead of Ty rank-1 updates)
+    dcc = np.matmul(alphas.transpose(2, 1, 0), dcraws.transpose(1, 0, 2)).transpose(1, 0, 2)
+    dcc = dcc + dpctx @ Wc_att.T
     demb = dxg @ P[p + '_W'].T + dxx @ P[p + '_Wx'].T
     return demb, dcc, dh
 
