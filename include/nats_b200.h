@@ -171,6 +171,14 @@ int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, fl
                              const int32_t* parent, int n_new, int len_cap, int hist_len, int dim);
 
 /* ---------------------------------------------------------------- diagnostics ------------------- */
+/* The library's internal GEMM engine, exposed for the parity tests: C = op(A).op(B) (+bias) (+C), row-major,
+ * path 0 = exact-fp32 FFMA kernels, path 1 = tcgen05 3xTF32 kernel with software loaders, path 2 = tcgen05 3xTF32
+ * kernel fed by TMA (needs 16-byte aligned operands, leading dimensions multiple of 4).  splitk > 1 writes splitk slabs
+ * of M*ldc floats to C (the consumer kernels sum them); batch > 1 uses the given strides. */
+int nats_debug_gemm(nats_ctx_t* ctx, void* stream, int path, int transA, int transB, int M, int N, int K,
+                    const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+                    int accumulate, int splitk, int batch, int64_t strideA, int64_t strideB, int64_t strideC);
+
 /* Per-kernel-class timing with CUDA events on the launch stream (eager launches only; keep it off while a step
  * is captured into a CUDA graph).  nats_profile_read synchronises the device and returns, per class, the summed
  * milliseconds, algorithmic flops / bytes declared at the launch sites, and the number of launches. */

@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of libnats_b200.so (declared in include/nats_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -30,7 +31,7 @@ const char* kNames[K_COUNT] = {
     "gemm_mid_tt", "gemm_smallm_nn", "gemm_smallm_nt", "gemm_smallm_tn", "gemm_smallm_tt", "gru_gates_fwd",
     "gru_gates_bwd", "att_scores", "att_context", "att_bwd_ctx", "att_bwd_dalpha", "att_bwd_softmax", "nll_rows",
     "dlogits", "softmax_sample", "colsum", "reduce_splits", "embedding", "elementwise", "optimizer", "beam",
-    "memset"};
+    "memset", "tc_gemm_3xtf32", "tc_gemm_3xtf32_skinny"};
 }  // namespace
 const char* kclass_name(int cls) { return (cls >= 0 && cls < K_COUNT) ? kNames[cls] : "?"; }
 bool prof_enabled() { return g_prof.on; }
@@ -86,6 +87,9 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     c->dev_scratch = nullptr;
     NATS_CUDA_OK(cudaMalloc(&c->dev_scratch, kCtxScratchFloats * sizeof(float)));
     int r = attention_setup(c);
+    if (r == 0) r = tc_gemm_setup();
+    if (r == 0) r = tma_gemm_setup();
+    gemm_set_tensor_cores(getenv("NATS_TC") ? atoi(getenv("NATS_TC")) : 2);
     if (r != 0) { cudaFree(c->dev_scratch); delete c; return r; }
     *out = c;
     return 0;
@@ -158,6 +162,28 @@ int nats_param_layout(const nats_dims_t* dims, nats_param_view_t* views, int64_t
     }
     if (total_floats) *total_floats = o.total;
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------ debug
+int nats_debug_gemm(nats_ctx_t* ctx, void* stream, int path, int transA, int transB, int M, int N, int K,
+                    const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+                    int accumulate, int splitk, int batch, int64_t strideA, int64_t strideB, int64_t strideC) {
+    NATS_REQUIRE(ctx && A && B && C, "null argument");
+    GemmProblem p = gemm_problem(A, lda, B, ldb, C, ldc, M, N, K);
+    p.bias = bias; p.accumulate = accumulate; p.batch = batch < 1 ? 1 : batch;
+    p.strideA = strideA; p.strideB = strideB; p.strideC = strideC;
+    if (splitk > 1) gemm_set_split(p, splitk, (long long)M * ldc);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (path == 1) return tc_gemm_launch(st, &p, 1, transA != 0, transB != 0);
+    if (path == 2) {
+        NATS_REQUIRE(tma_gemm_eligible(&p, 1), "operands not TMA-compatible (alignment)");
+        return tma_gemm_launch(st, &p, 1, transA != 0, transB != 0);
+    }
+    const int keep = gemm_get_tensor_cores();
+    gemm_set_tensor_cores(0);
+    const int r = gemm_launch(st, &p, 1, transA != 0, transB != 0, GEMM_CFG_AUTO);
+    gemm_set_tensor_cores(keep);
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------ profiling

@@ -257,8 +257,26 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int nsplit,
 
 }  // namespace
 
+static int g_use_tc = 2;      // 0: FFMA, 1: tcgen05 with software loaders, 2: tcgen05 fed by TMA where possible
+void gemm_set_tensor_cores(int on) { g_use_tc = on; }
+int gemm_get_tensor_cores() { return g_use_tc; }
+
+// is this group worth a 128-row tensor-core tile?  (tiny problems stay on the FFMA kernels)
+static bool tc_eligible(const GemmProblem* probs, int count) {
+    if (!g_use_tc) return false;
+    for (int i = 0; i < count; ++i) {
+        const int big = probs[i].M > probs[i].N ? probs[i].M : probs[i].N;
+        if (big < 128 || probs[i].K < 32) return false;
+    }
+    return true;
+}
+
 int gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool transA, bool transB, int cfg) {
     NATS_REQUIRE(count >= 1 && count <= kGemmMaxGroup, "gemm group size");
+    if (tc_eligible(probs, count)) {
+        if (g_use_tc >= 2 && tma_gemm_eligible(probs, count)) return tma_gemm_launch(st, probs, count, transA, transB);
+        return tc_gemm_launch(st, probs, count, transA, transB);
+    }
     GemmGroup grp;
     memset(&grp, 0, sizeof(grp));
     grp.count = count;
@@ -294,12 +312,22 @@ int gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool trans
 int gemm_step_cfg(int M) { return M <= 32 ? GEMM_CFG_SMALLM : GEMM_CFG_MID; }
 
 int gemm_pick_split(const nats_ctx* ctx, int M, int N, int K) {
-    const int bm = (M <= 32) ? 32 : 64, bn = (M <= 32) ? 128 : 64;
-    const int tiles = cdiv(N, bn) * cdiv(M, bm);
+    int tiles;
+    if (g_use_tc && (M >= 128 || N >= 128) && K >= 32) {
+        const int a = M > N ? M : N, b = M > N ? N : M;      // 128-row side / N side of the tensor-core tile
+        const int bn = b <= 32 ? 32 : (b <= 64 ? 64 : 128);
+        tiles = cdiv(a, 128) * cdiv(b, bn);
+    } else {
+        const int bm = (M <= 32) ? 32 : 64, bn = (M <= 32) ? 128 : 64;
+        tiles = cdiv(N, bn) * cdiv(M, bm);
+    }
     int s = ctx->num_sms / (tiles > 0 ? tiles : 1);
     s = min(s, K / 64);
     s = min(s, kGemmMaxSplit);
-    return max(s, 1);
+    s = max(s, 1);
+    // chunks are multiples of 32: drop splits that would be empty
+    const int chunk = ((cdiv(K, s) + 31) / 32) * 32;
+    return max(cdiv(K, chunk), 1);
 }
 
 int reduce_splits(cudaStream_t st, const float* part, int nsplit, long long strideP, int M, int N, int ldp,
@@ -319,14 +347,26 @@ int reduce_splits(cudaStream_t st, const float* part, int nsplit, long long stri
 int gemm_auto(const nats_ctx* ctx, cudaStream_t st, GemmProblem p, bool transA, bool transB, float* scratch,
               long long scratch_floats) {
     if (p.M == 0 || p.N == 0) return 0;
-    int cfg, bm, bn;
-    if (p.M <= 32) { cfg = GEMM_CFG_SMALLM; bm = 32; bn = 128; }
-    else if (p.M >= 512 && p.N >= 512) { cfg = GEMM_CFG_BIG; bm = 128; bn = 128; }
-    else { cfg = GEMM_CFG_MID; bm = 64; bn = 64; }
-    const long long tiles = (long long)cdiv(p.M, bm) * cdiv(p.N, bn) * p.batch;
+    const bool tc = tc_eligible(&p, 1);
+    int cfg = GEMM_CFG_AUTO;
+    long long tiles;
+    if (tc) {
+        const int a = p.M > p.N ? p.M : p.N, b = p.M > p.N ? p.N : p.M;
+        const bool swapped = p.M < 128 && p.N > p.M;
+        const int nb = swapped ? p.M : p.N, ma = swapped ? p.N : p.M;
+        (void)a; (void)b;
+        const int bn = nb <= 32 ? 32 : (nb <= 64 ? 64 : 128);
+        tiles = (long long)cdiv(ma, 128) * cdiv(nb, bn) * p.batch;
+    } else {
+        int bm, bn;
+        if (p.M <= 32) { cfg = GEMM_CFG_SMALLM; bm = 32; bn = 128; }
+        else if (p.M >= 512 && p.N >= 512) { cfg = GEMM_CFG_BIG; bm = 128; bn = 128; }
+        else { cfg = GEMM_CFG_MID; bm = 64; bn = 64; }
+        tiles = (long long)cdiv(p.M, bm) * cdiv(p.N, bn) * p.batch;
+    }
     int splits = 1;
     if (p.batch == 1 && tiles < ctx->num_sms && p.K >= 256 && scratch != nullptr) {
-        long long want = (2LL * ctx->num_sms + tiles - 1) / tiles;
+        long long want = ((tc ? 1LL : 2LL) * ctx->num_sms + tiles - 1) / tiles;
         if (want > p.K / 128) want = p.K / 128;
         splits = (int)want;
         splits = min(splits, kGemmMaxSplit);

@@ -58,6 +58,16 @@ inline void gemm_set_split(GemmProblem& p, int splits, long long strideP) {
     p.strideP = strideP;
 }
 
+// tensor-core path (tc_gemm.cu): same contract as gemm_launch, 3xTF32 on tcgen05
+int tc_gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool transA, bool transB);
+int tc_gemm_setup();
+// TMA-fed variant (tma_gemm.cu): needs 16-byte aligned operands with leading dimensions multiple of 4
+int tma_gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool transA, bool transB);
+bool tma_gemm_eligible(const GemmProblem* probs, int count);
+int tma_gemm_setup();
+void gemm_set_tensor_cores(int on);     // 1 (default): GEMM-shaped work goes to tcgen05; 0: exact-fp32 FFMA kernels
+int gemm_get_tensor_cores();
+
 // Low-level launch: all problems share transposition flags and tile configuration.
 int gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool transA, bool transB, int cfg);
 

@@ -24,6 +24,8 @@ enum KClass {
     K_OPTIM,
     K_BEAM,
     K_MEMSET,
+    K_TC_GEMM,           // tcgen05 3xTF32, 128 x 128 tiles
+    K_TC_GEMM_SKINNY,    // tcgen05 3xTF32, swapped roles (batch on the N side)
     K_COUNT
 };
 

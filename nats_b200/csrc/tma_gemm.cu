@@ -1,0 +1,474 @@
+// tma_gemm.cu -- tcgen05 3xTF32 GEMM fed by the Tensor Memory Accelerator.
+//
+//   TMA (cp.async.bulk.tensor.2d/3d, SWIZZLE_128B) lands RAW fp32 operand tiles straight in the canonical UMMA
+//   shared-memory layout -- K-major for K-contiguous sources, MN-major for row-contiguous sources, so no transposed
+//   copies of anything are ever made.  The tensor core truncates fp32 words to tf32 (verified on B200), hence the raw
+//   tile IS the "hi" operand; eight warps only compute the residual tiles  lo = x - trunc_tf32(x)  in shared memory.
+//       D += A_lo.B_raw + A_raw.B_lo          (correction accumulator)
+//       D += A_raw.B_raw                      (three round-robin main accumulators: short truncation chains)
+//   warp 8 lane 0 : TMA producer        (waits empty[s], arms tma_full[s] with expect_tx, issues the box copies)
+//   warps 0-7     : residual pass        (wait tma_full[s]; raw -> lo, 16-byte vectors; fence.proxy.async; arrive mma_full[s])
+//   warp 9 lane 0 : tcgen05.mma issuer   (wait mma_full[s]; 4 k-steps x 3 UMMA 128 x BN x 8; tcgen05.commit -> empty[s])
+//   warps 8-11    : epilogue             (tcgen05.ld of the four accumulators, fp32 sum, bias/accumulate/slab store)
+// Requirements: 16-byte aligned base pointers and leading dimensions that are multiples of 4 floats (TMA strides);
+// anything else is served by the software-loader kernel in tc_gemm.cu.
+#include <cuda.h>
+
+#include <unordered_map>
+#include <string>
+
+#include "gemm.cuh"
+
+namespace nats {
+
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kSplitThreads = 256;
+constexpr int kBlockK = 32;
+constexpr int kMaxGroup = 2;
+
+struct TmaProblem {
+    float* C;
+    const float* bias;
+    int Ma, Nb, K;
+    long long c_rs, c_cs;
+    int batch;
+    long long sC;
+    int splitk, kchunk;
+    long long strideP;
+    int accumulate;
+    int bias_on_a;
+};
+struct alignas(64) TmaGroup {
+    CUtensorMap mapA[kMaxGroup];
+    CUtensorMap mapB[kMaxGroup];
+    TmaProblem p[kMaxGroup];
+    int zstart[kMaxGroup + 1];
+    int count;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor), SWIZZLE_128B
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {      // rows of 128 B (32 k), 8-row groups 1024 B apart
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B flavour (cutlass sm100_common.inl:92): rows of 128 B
+// (32 mn) per k, 32-byte chunks XOR (k & 3), K atoms of 4 rows (SBO = 512 B); 32-row mn blocks 4096 B apart (LBO).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ float resid(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_constant__ TmaGroup grp) {
+    constexpr uint32_t kABytes = 128 * 128, kBBytes = BN * 128;
+    constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+    constexpr uint32_t kTmemCols = 4 * BN;
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t tma_full[STAGES];
+    __shared__ __align__(8) uint64_t mma_full[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    int z = blockIdx.z, g = 0;
+    if (grp.count > 1 && z >= grp.zstart[1]) g = 1;
+    const TmaProblem& P = grp.p[g];
+    const CUtensorMap* mapA = &grp.mapA[g];
+    const CUtensorMap* mapB = &grp.mapB[g];
+    z -= grp.zstart[g];
+    const int split = z % P.splitk, batch = z / P.splitk;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+    if (m0 >= P.Ma || n0 >= P.Nb) return;
+
+    const int kbeg = split * P.kchunk;
+    const int kend = min(P.K, kbeg + P.kchunk);
+    const int nkb = (kend > kbeg) ? (kend - kbeg + kBlockK - 1) / kBlockK : 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&tma_full[s], 1);
+            mbar_init(&mma_full[s], kSplitThreads);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (warp < 8) {
+        // ===================== residual pass: lo = raw - trunc_tf32(raw) =====================
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&tma_full[s], (uint32_t)((kb / STAGES) & 1));
+            const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
+#pragma unroll
+            for (int i = 0; i < (int)(kABytes / 16) / kSplitThreads; ++i) {
+                const uint32_t off = (uint32_t)(tid + i * kSplitThreads) * 16u;
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + off));
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + kABytes + off), "f"(resid(v.x)),
+                             "f"(resid(v.y)), "f"(resid(v.z)), "f"(resid(v.w))
+                             : "memory");
+            }
+#pragma unroll
+            for (int i = 0; i < ((int)(kBBytes / 16) + kSplitThreads - 1) / kSplitThreads; ++i) {
+                const uint32_t q = (uint32_t)(tid + i * kSplitThreads);
+                if (q < kBBytes / 16) {
+                    const uint32_t off = q * 16u;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + 2 * kABytes + off));
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + 2 * kABytes + kBBytes + off),
+                                 "f"(resid(v.x)), "f"(resid(v.y)), "f"(resid(v.z)), "f"(resid(v.w))
+                                 : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&mma_full[s]);
+        }
+    } else {
+        if (warp == 8 && lane == 0) {
+            // ===================== TMA producer =====================
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty_bar[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
+                const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
+                const int k0 = kbeg + kb * kBlockK;
+                mbar_expect_tx(&tma_full[s], kABytes + kBBytes);
+                if (A_MN) {
+#pragma unroll
+                    for (int bi = 0; bi < 4; ++bi) tma_load_3d(st + bi * 4096, mapA, &tma_full[s], m0 + 32 * bi, k0, batch);
+                } else {
+                    tma_load_3d(st, mapA, &tma_full[s], k0, m0, batch);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int bi = 0; bi < BN / 32; ++bi)
+                        tma_load_3d(st + 2 * kABytes + bi * 4096, mapB, &tma_full[s], n0 + 32 * bi, k0, batch);
+                } else {
+                    tma_load_3d(st + 2 * kABytes, mapB, &tma_full[s], k0, n0, batch);
+                }
+            }
+        } else if (warp == 9 && lane == 0) {
+            // ===================== MMA issuer =====================
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&mma_full[s], (uint32_t)((kb / STAGES) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
+                const uint64_t a_raw = A_MN ? desc_mnmajor(st) : desc_kmajor(st);
+                const uint64_t a_lo = A_MN ? desc_mnmajor(st + kABytes) : desc_kmajor(st + kABytes);
+                const uint64_t b_raw = B_MN ? desc_mnmajor(st + 2 * kABytes) : desc_kmajor(st + 2 * kABytes);
+                const uint64_t b_lo = B_MN ? desc_mnmajor(st + 2 * kABytes + kBBytes) : desc_kmajor(st + 2 * kABytes + kBBytes);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t adv_a = (uint64_t)((A_MN ? kk * 1024 : kk * 32) >> 4);
+                    const uint64_t adv_b = (uint64_t)((B_MN ? kk * 1024 : kk * 32) >> 4);
+                    const int gstep = kb * 4 + kk;
+                    umma_tf32(tmem_d + 3u * BN, a_lo + adv_a, b_raw + adv_b, idesc, gstep != 0 ? 1u : 0u);
+                    umma_tf32(tmem_d + 3u * BN, a_raw + adv_a, b_lo + adv_b, idesc, 1u);
+                    umma_tf32(tmem_d + (uint32_t)(gstep % 3) * BN, a_raw + adv_a, b_raw + adv_b, idesc, gstep >= 3 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&accum_bar);
+        }
+        __syncwarp();
+        // ===================== epilogue (warps 8-11 <-> TMEM lanes 32q..32q+31) =====================
+        const int q = warp - 8;
+        const int i = m0 + q * 32 + lane;
+        float* __restrict__ C = P.C + (long long)batch * P.sC + (long long)split * P.strideP;
+        const bool add_bias = (P.bias != nullptr) && (split == 0);
+        if (nkb > 0) {
+            mbar_wait(&accum_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const float bias_a = (add_bias && P.bias_on_a && i < P.Ma) ? __ldg(P.bias + i) : 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            if (n0 + c0 >= P.Nb) break;
+            float r[16];
+            if (nkb > 0) {
+                uint32_t t0[16], t1[16], t2[16], t3[16];
+                const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                tmem_ld16(ta, t0);
+                tmem_ld16(ta + BN, t1);
+                tmem_ld16(ta + 2 * BN, t2);
+                tmem_ld16(ta + 3 * BN, t3);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                    r[t] = ((__uint_as_float(t0[t]) + __uint_as_float(t1[t])) + __uint_as_float(t2[t])) + __uint_as_float(t3[t]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) r[t] = 0.f;
+            }
+            if (i < P.Ma) {
+                float* crow = C + (long long)i * P.c_rs;
+                const bool vec = (P.c_cs == 1) && ((P.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                                 (n0 + c0 + 15 < P.Nb);
+                if (vec) {
+#pragma unroll
+                    for (int t = 0; t < 16; t += 4) {
+                        const int j = n0 + c0 + t;
+                        float4 o = make_float4(r[t] + bias_a, r[t + 1] + bias_a, r[t + 2] + bias_a, r[t + 3] + bias_a);
+                        if (add_bias && !P.bias_on_a) {
+                            o.x += __ldg(P.bias + j); o.y += __ldg(P.bias + j + 1);
+                            o.z += __ldg(P.bias + j + 2); o.w += __ldg(P.bias + j + 3);
+                        }
+                        float4* cp = reinterpret_cast<float4*>(crow + j);
+                        if (P.accumulate) {
+                            const float4 old = *cp;
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *cp = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const int j = n0 + c0 + t;
+                        if (j < P.Nb) {
+                            float o = r[t] + bias_a;
+                            if (add_bias && !P.bias_on_a) o += __ldg(P.bias + j);
+                            float* cp = crow + (long long)j * P.c_cs;
+                            if (P.accumulate) o += *cp;
+                            *cp = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int BN, int STAGES>
+constexpr size_t smem_bytes() { return (size_t)STAGES * (2 * 128 * 128 + 2 * BN * 128) + 1024; }
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+struct MapKey {
+    const void* ptr; long long inner, outer, ld, batch, bstride; int box_outer; int mn;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && batch == o.batch &&
+               bstride == o.bstride && box_outer == o.box_outer && mn == o.mn;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        auto mix = [&](long long v) { h ^= std::hash<long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.inner); mix(k.outer); mix(k.ld); mix(k.batch); mix(k.bstride); mix(k.box_outer); mix(k.mn);
+        return h;
+    }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 3-D map over a (batch, outer, inner) fp32 array; box = (1, box_outer, 32 floats = one 128-byte swizzle row)
+int get_map(const float* ptr, long long inner, long long outer, long long ld, long long batch, long long bstride,
+            int box_outer, bool mn_major, CUtensorMap* out) {
+    MapKey key{ptr, inner, outer, ld, batch, bstride, box_outer, mn_major ? 1 : 0};
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    if (g_maps.size() > (1u << 16)) g_maps.clear();
+    cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batch < 1 ? 1 : batch)};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? bstride : (long long)outer * ld) * 4};
+    if (gstr[1] == 0) gstr[1] = 16;
+    cuuint32_t box[3] = {32, (cuuint32_t)box_outer, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld outer=%lld ld=%lld batch=%lld", (int)r, ptr, inner,
+                  outer, ld, batch);
+        return 1;
+    }
+    g_maps.emplace(key, m);
+    *out = m;
+    return 0;
+}
+
+template <int BN, int STAGES>
+int launch_bn(cudaStream_t st, const TmaGroup& grp, bool a_mn, bool b_mn, dim3 grid, double flops, double bytes) {
+    ProfScope ps(st, BN <= 64 ? K_TC_GEMM_SKINNY : K_TC_GEMM, flops, bytes);
+    const size_t sm = smem_bytes<BN, STAGES>();
+    if (!a_mn && !b_mn) tma_gemm_kernel<BN, STAGES, false, false><<<grid, kThreads, sm, st>>>(grp);
+    else if (!a_mn && b_mn) tma_gemm_kernel<BN, STAGES, false, true><<<grid, kThreads, sm, st>>>(grp);
+    else if (a_mn && !b_mn) tma_gemm_kernel<BN, STAGES, true, false><<<grid, kThreads, sm, st>>>(grp);
+    else tma_gemm_kernel<BN, STAGES, true, true><<<grid, kThreads, sm, st>>>(grp);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+
+template <int BN, int STAGES>
+int set_attrs() {
+    const int sm = (int)smem_bytes<BN, STAGES>();
+    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, STAGES, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, STAGES, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, STAGES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, STAGES, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    return 0;
+}
+
+}  // namespace
+
+int tma_gemm_setup() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    NATS_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (fn == nullptr || q != cudaDriverEntryPointSuccess) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return 1;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    NATS_TRY((set_attrs<32, 4>()));
+    NATS_TRY((set_attrs<64, 4>()));
+    NATS_TRY((set_attrs<128, 3>()));
+    return 0;
+}
+
+// can this group be served by TMA?  (16-byte aligned pointers, leading dimensions multiple of 4 floats)
+bool tma_gemm_eligible(const GemmProblem* probs, int count) {
+    if (g_encode == nullptr || count > kMaxGroup) return false;
+    for (int i = 0; i < count; ++i) {
+        const GemmProblem& q = probs[i];
+        if ((q.lda & 3) || (q.ldb & 3)) return false;
+        if ((reinterpret_cast<uintptr_t>(q.A) & 15) || (reinterpret_cast<uintptr_t>(q.B) & 15)) return false;
+        if (q.batch > 1 && ((q.strideA & 3) || (q.strideB & 3))) return false;
+        if (q.M < 1 || q.N < 1 || q.K < 1) return false;
+    }
+    return true;
+}
+
+int tma_gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool transA, bool transB) {
+    NATS_REQUIRE(count >= 1 && count <= kMaxGroup, "tma gemm group size");
+    TmaGroup grp;
+    memset(&grp, 0, sizeof(grp));
+    grp.count = count;
+    int maxM = 0, maxN = 0;
+    for (int i = 0; i < count; ++i) { maxM = max(maxM, probs[i].M); maxN = max(maxN, probs[i].N); }
+    const bool swapped = maxM < 128 && maxN > maxM;
+    const int nb_dim = swapped ? maxM : maxN;
+    const int BN = nb_dim <= 32 ? 32 : (nb_dim <= 64 ? 64 : 128);
+    // op(A)(m,k): transA ? m contiguous : k contiguous.  op(B)(k,n): transB ? k contiguous : n contiguous.
+    const bool opa_mn = transA, opb_mn = !transB;
+    const bool a_mn = swapped ? opb_mn : opa_mn;      // the 128-row side operand
+    const bool b_mn = swapped ? opa_mn : opb_mn;
+    int z = 0, ga = 0, gb = 0;
+    double flops = 0.0, bytes = 0.0;
+    for (int i = 0; i < count; ++i) {
+        const GemmProblem& q = probs[i];
+        NATS_REQUIRE(q.splitk >= 1 && q.batch >= 1 && (q.splitk == 1 || !q.accumulate), "tma gemm split/batch");
+        TmaProblem& t = grp.p[i];
+        // maps: K-major operand -> inner = K, outer = rows; MN-major -> inner = rows, outer = K
+        CUtensorMap ma, mb;
+        NATS_TRY(get_map(q.A, opa_mn ? q.M : q.K, opa_mn ? q.K : q.M, q.lda, q.batch, q.strideA,
+                         opa_mn ? 32 : (swapped ? BN : 128), opa_mn, &ma));
+        NATS_TRY(get_map(q.B, opb_mn ? q.N : q.K, opb_mn ? q.K : q.N, q.ldb, q.batch, q.strideB,
+                         opb_mn ? 32 : (swapped ? 128 : BN), opb_mn, &mb));
+        if (!swapped) {
+            grp.mapA[i] = ma; grp.mapB[i] = mb;
+            t.Ma = q.M; t.Nb = q.N; t.c_rs = q.ldc; t.c_cs = 1; t.bias_on_a = 0;
+        } else {
+            grp.mapA[i] = mb; grp.mapB[i] = ma;
+            t.Ma = q.N; t.Nb = q.M; t.c_rs = 1; t.c_cs = q.ldc; t.bias_on_a = 1;
+        }
+        t.C = q.C; t.bias = q.bias; t.K = q.K; t.batch = q.batch; t.sC = q.strideC;
+        t.splitk = q.splitk;
+        t.kchunk = ((q.kchunk + 31) / 32) * 32;
+        if (q.splitk > 1) t.kchunk = ((cdiv(q.K, q.splitk) + 31) / 32) * 32;
+        if (t.kchunk <= 0) t.kchunk = 32;
+        t.strideP = q.strideP; t.accumulate = q.accumulate;
+        grp.zstart[i] = z;
+        z += q.batch * q.splitk;
+        ga = max(ga, cdiv(t.Ma, 128));
+        gb = max(gb, cdiv(t.Nb, BN));
+        flops += 2.0 * q.M * q.N * q.K * q.batch;
+        bytes += 4.0 * q.batch * ((double)q.M * q.K + (double)q.K * q.N + (double)q.M * q.N * q.splitk);
+    }
+    grp.zstart[count] = z;
+    for (int i = count; i < kMaxGroup; ++i) grp.zstart[i + 1] = z;
+    if (ga == 0 || gb == 0 || z == 0) return 0;
+    dim3 grid(ga, gb, z);
+    if (BN == 32) return launch_bn<32, 4>(st, grp, a_mn, b_mn, grid, flops, bytes);
+    if (BN == 64) return launch_bn<64, 4>(st, grp, a_mn, b_mn, grid, flops, bytes);
+    return launch_bn<128, 3>(st, grp, a_mn, b_mn, grid, flops, bytes);
+}
+
+}  // namespace nats
