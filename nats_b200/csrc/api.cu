@@ -31,7 +31,7 @@ const char* kNames[K_COUNT] = {
     "gemm_mid_tt", "gemm_smallm_nn", "gemm_smallm_nt", "gemm_smallm_tn", "gemm_smallm_tt", "gru_gates_fwd",
     "gru_gates_bwd", "att_scores", "att_context", "att_bwd_ctx", "att_bwd_dalpha", "att_bwd_softmax", "nll_rows",
     "dlogits", "softmax_sample", "colsum", "reduce_splits", "embedding", "elementwise", "optimizer", "beam",
-    "memset", "tc_gemm_3xtf32", "tc_gemm_3xtf32_skinny"};
+    "memset", "tc_gemm_3xtf32", "tc_gemm_3xtf32_skinny", "gru_step_fwd_fused", "gru_step_bwd_fused"};
 }  // namespace
 const char* kclass_name(int cls) { return (cls >= 0 && cls < K_COUNT) ? kNames[cls] : "?"; }
 bool prof_enabled() { return g_prof.on; }
@@ -89,6 +89,8 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     int r = attention_setup(c);
     if (r == 0) r = tc_gemm_setup();
     if (r == 0) r = tma_gemm_setup();
+    if (r == 0) r = gru_step_setup();
+    gru_step_enable(getenv("NATS_FUSED_STEP") ? atoi(getenv("NATS_FUSED_STEP")) : 0);
     gemm_set_tensor_cores(getenv("NATS_TC") ? atoi(getenv("NATS_TC")) : 2);
     if (r != 0) { cudaFree(c->dev_scratch); delete c; return r; }
     *out = c;
@@ -325,6 +327,7 @@ int nats_sampler_init(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, co
     e.cc = ctx_out; e.ctxsum = w.ctxsum; e.xlen = w.xlen; e.xinv = w.xinv; e.ctx_mean = w.ctx_mean;
     e.init_state = init_state; e.part_a = w.part_a;
     e.gemm_scratch = w.gemm_scratch; e.gemm_scratch_floats = w.gemm_scratch_floats;
+    e.step_slab = w.step_slab; e.step_counters = w.step_counters; e.step_counter_ints = w.step_counter_ints;
     NATS_TRY(encoder_forward(ctx, st, *dims, params, x, nullptr, Tx, n, e));      // no masks (nats.py:801-804, 810)
     if (pctx_out) {
         const ParamOff o = param_offsets(*dims);
@@ -387,6 +390,10 @@ int nats_sampler_next(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, co
     s.alpha_out = alphaT; s.acc_alpha_out = acc_alpha_out; s.craw_out = w.craw; s.ctx_out = ctxs;
     s.acc_ctx_out = acc_ctx_out; s.h2 = state_out;
     s.part_a = w.part_a; s.part_b = w.part_b; s.part_c = w.part_c; s.part_d = w.part_d;
+    if (gru_step_eligible(n, D)) {
+        NATS_CUDA_OK(memset_async(st, w.step_counters, 0, (size_t)w.step_counter_ints * sizeof(int)));
+        s.step_slab = w.step_slab; s.step_counters = w.step_counters;
+    }
     NATS_TRY(decoder_step_forward(ctx, st, *dims, params, s));
 
     // readout (nats.py:850-861)

@@ -311,7 +311,7 @@ int gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool trans
 
 int gemm_step_cfg(int M) { return M <= 32 ? GEMM_CFG_SMALLM : GEMM_CFG_MID; }
 
-int gemm_pick_split(const nats_ctx* ctx, int M, int N, int K) {
+int gemm_pick_split(const nats_ctx* ctx, int M, int N, int K, int groups) {
     int tiles;
     if (g_use_tc && (M >= 128 || N >= 128) && K >= 32) {
         const int a = M > N ? M : N, b = M > N ? N : M;      // 128-row side / N side of the tensor-core tile
@@ -321,6 +321,7 @@ int gemm_pick_split(const nats_ctx* ctx, int M, int N, int K) {
         const int bm = (M <= 32) ? 32 : 64, bn = (M <= 32) ? 128 : 64;
         tiles = cdiv(N, bn) * cdiv(M, bm);
     }
+    tiles *= (groups > 0 ? groups : 1);          // grouped launches (both encoder directions) share the machine
     int s = ctx->num_sms / (tiles > 0 ? tiles : 1);
     s = min(s, K / 64);
     s = min(s, kGemmMaxSplit);

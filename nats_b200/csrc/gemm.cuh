@@ -73,7 +73,7 @@ int gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool trans
 
 // Tile configuration and number of K-splits that fill the machine for a skinny (M = batch) weight-streaming product.
 int gemm_step_cfg(int M);
-int gemm_pick_split(const nats_ctx* ctx, int M, int N, int K);
+int gemm_pick_split(const nats_ctx* ctx, int M, int N, int K, int groups = 1);
 
 // Convenience: single problem, picks the tile configuration; if the problem would launch too few CTAs and K
 // is deep, runs split-K into `scratch` (scratch_floats available) and reduces (+bias, +accumulate).

@@ -24,11 +24,33 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
         NATS_TRY(gemm_launch(st, pr, 2, false, false, GEMM_CFG_AUTO));
     }
     NATS_CUDA_OK(memset_async(st, e.ctxsum, 0, (size_t)n * C * sizeof(float)));
-    const int S = gemm_pick_split(ctx, n, D3, D);
+    const int S = gemm_pick_split(ctx, n, D3, D, 2);
     const int cfg = gemm_step_cfg(n);
     const long long strideP = 2LL * n * D3;
+    const bool fused = gru_step_eligible(n, D) && e.step_slab != nullptr;
+    if (fused) NATS_CUDA_OK(memset_async(st, e.step_counters, 0, (size_t)e.step_counter_ints * sizeof(int)));
     for (int s = 0; s < Tx; ++s) {
         const int pf = s, pb = Tx - 1 - s;      // source positions handled by the forward / backward direction
+        if (fused && s > 0) {                   // product + split-K fix-up + gates of both directions in ONE launch
+            GruStepFwd f[2];
+            memset(f, 0, sizeof(f));
+            for (int dir = 0; dir < 2; ++dir) {
+                const int pos = dir == 0 ? pf : pb;
+                const int prev = dir == 0 ? pf - 1 : pb + 1;
+                f[dir].Ucat = params + o.enc[dir].Ucat;
+                f[dir].xproj = e.xproj[dir] + (long long)pos * n * D3;
+                f[dir].h_prev = e.cc + (long long)prev * n * C + dir * D; f[dir].ld_hprev = C;
+                f[dir].mask = x_mask ? x_mask + (long long)pos * n : nullptr;
+                f[dir].h_out = e.cc + (long long)pos * n * C + dir * D; f[dir].ld_hout = C;
+                if (e.r[dir]) {
+                    const long long so = (long long)pos * n * D;
+                    f[dir].r = e.r[dir] + so; f[dir].u = e.u[dir] + so; f[dir].c = e.c[dir] + so; f[dir].p = e.p[dir] + so;
+                }
+                f[dir].ctxsum = e.ctxsum + dir * D; f[dir].ld_ctxsum = C;
+            }
+            NATS_TRY(gru_step_fwd(ctx, st, f, 2, n, D, e.step_slab, e.step_counters));
+            continue;
+        }
         if (s > 0) {                                                                     // nats.py:337, 345
             GemmProblem q[2];
             q[0] = gemm_problem(e.cc + (long long)(pf - 1) * n * C, C, params + o.enc[0].Ucat, D3, e.part_a, D3, n, D3, D);
@@ -83,7 +105,15 @@ int decoder_step_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t
     const int S1 = gemm_pick_split(ctx, n, D3, D);
     const int S2 = gemm_pick_split(ctx, n, D3, C);
     const long long sp3 = (long long)n * D3;
-    {   // GRU_2 recurrent product (nats.py:505, 512)
+    if (gru_step_eligible(n, D) && s.step_slab != nullptr) {      // GRU_2 in one fused launch (nats.py:505-518)
+        GruStepFwd f;
+        memset(&f, 0, sizeof(f));
+        f.Ucat = params + o.dec.Ucat; f.xproj = s.xproj;
+        f.h_prev = s.h_prev; f.ld_hprev = D; f.mask = s.ymask;
+        f.h_out = s.h1; f.ld_hout = D;
+        f.r = s.r1; f.u = s.u1; f.c = s.c1; f.p = s.p1;
+        NATS_TRY(gru_step_fwd(ctx, st, &f, 1, n, D, s.step_slab, s.step_counters));
+    } else {   // GRU_2 recurrent product (nats.py:505, 512)
         GemmProblem q = gemm_problem(s.h_prev, D, params + o.dec.Ucat, D3, s.part_b, D3, n, D3, D);
         gemm_set_split(q, S1, sp3);
         NATS_TRY(gemm_launch(st, &q, 1, false, false, cfg));
@@ -155,6 +185,7 @@ int train_encoder_fwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
     e.cc = w.cc; e.ctxsum = w.ctxsum; e.xlen = w.xlen; e.xinv = w.xinv; e.ctx_mean = w.ctx_mean;
     e.init_state = w.init_state; e.part_a = w.part_a;
     e.gemm_scratch = w.gemm_scratch; e.gemm_scratch_floats = w.gemm_scratch_floats;
+    e.step_slab = w.step_slab; e.step_counters = w.step_counters; e.step_counter_ints = w.step_counter_ints;
     return encoder_forward(ctx, st, d, params, x, x_mask, Tx, B, e);
 }
 
@@ -176,6 +207,7 @@ int train_decoder_fwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
         p.bias = params + o.b_att;
         NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
     }
+    NATS_CUDA_OK(memset_async(st, w.step_counters, 0, (size_t)w.step_counter_ints * sizeof(int)));
     NATS_CUDA_OK(memset_async(st, w.d_accalpha, 0, (size_t)B * Tx * sizeof(float)));   // nats.py:599-603
     NATS_CUDA_OK(memset_async(st, w.d_accctx, 0, (size_t)B * C * sizeof(float)));
     for (int t = 0; t < Ty; ++t) {
@@ -198,6 +230,7 @@ int train_decoder_fwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
         s.craw_out = w.d_craw + rC; s.ctx_out = w.d_ctx + rC;
         s.r2 = w.d_r2 + rD; s.u2 = w.d_u2 + rD; s.c2 = w.d_c2 + rD; s.p2 = w.d_p2 + rD; s.h2 = w.d_h2 + rD;
         s.part_a = w.part_a; s.part_b = w.part_b; s.part_c = w.part_c; s.part_d = w.part_d;
+        s.step_slab = w.step_slab; s.step_counters = w.step_counters;
         NATS_TRY(decoder_step_forward(ctx, st, d, params, s));
     }
     return 0;

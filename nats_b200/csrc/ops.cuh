@@ -51,6 +51,32 @@ struct GateBwd {
 };
 int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, int D);
 
+// ------------------------------------------------------------------ fused recurrent step (gru_step.cu)
+// One launch = tcgen05 product with the packed recurrent weights + split-K fix-up + the gate arithmetic above.
+struct GruStepFwd {
+    const float* Ucat;          // [D, 3D] = [U | Ux]
+    const float* xproj;         // [B,3D] input projection incl. biases
+    const float* h_prev; int ld_hprev;
+    const float* mask;          // [B] or NULL
+    float* h_out; int ld_hout;
+    float* r; float* u; float* c; float* p;     // save slots or NULL
+    float* ctxsum; int ld_ctxsum;               // or NULL
+};
+struct GruStepBwd {
+    const float* Ucat;
+    const float* dG_next;       // [B,3D]: gate derivatives of the step processed just before (time t+1)
+    GateBwd g;                  // arguments of THIS step's gate backward (part / part2 fields unused)
+};
+bool gru_step_eligible(int B, int D);
+void gru_step_enable(int on);
+long long gru_step_slab_floats(int B, int D);
+long long gru_step_counter_ints(int D);
+int gru_step_setup();
+int gru_step_fwd(const nats_ctx* ctx, cudaStream_t st, const GruStepFwd* dirs, int ndir, int B, int D, float* slab,
+                 int* counters);
+int gru_step_bwd(const nats_ctx* ctx, cudaStream_t st, const GruStepBwd* dirs, int ndir, int B, int D, float* slab,
+                 int* counters);
+
 // ------------------------------------------------------------------ small elementwise / reductions
 int tanh_inplace(cudaStream_t st, float* x, long long n);
 // dst[i] = g[i] * (1 - y[i]^2)

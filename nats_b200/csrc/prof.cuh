@@ -26,6 +26,8 @@ enum KClass {
     K_MEMSET,
     K_TC_GEMM,           // tcgen05 3xTF32, 128 x 128 tiles
     K_TC_GEMM_SKINNY,    // tcgen05 3xTF32, swapped roles (batch on the N side)
+    K_GRU_STEP_FWD,      // fused recurrent step: tcgen05 GEMM + split-K fix-up + gates
+    K_GRU_STEP_BWD,
     K_COUNT
 };
 

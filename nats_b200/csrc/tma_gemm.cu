@@ -18,6 +18,7 @@
 #include <string>
 
 #include "gemm.cuh"
+#include "tc_common.cuh"
 
 namespace nats {
 
@@ -48,78 +49,22 @@ struct alignas(64) TmaGroup {
     int count;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor), SWIZZLE_128B
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {      // rows of 128 B (32 k), 8-row groups 1024 B apart
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B flavour (cutlass sm100_common.inl:92): rows of 128 B
-// (32 mn) per k, 32-byte chunks XOR (k & 3), K atoms of 4 rows (SBO = 512 B); 32-row mn blocks 4096 B apart (LBO).
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ float resid(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+using namespace tc;
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int NR, int NL, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_constant__ TmaGroup grp) {
+    // shared memory: NR raw stages [A_raw 16 KB | B_raw BN*128] (filled by TMA, deep: covers the TMA latency) and
+    //                NL residual stages [A_lo | B_lo] (written by the residual warps, shallow: only lives until its MMAs retire)
     constexpr uint32_t kABytes = 128 * 128, kBBytes = BN * 128;
-    constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+    constexpr uint32_t kRawStage = kABytes + kBBytes;
+    constexpr uint32_t kLoBase = NR * kRawStage;
     constexpr uint32_t kTmemCols = 4 * BN;
 
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t tma_full[STAGES];
-    __shared__ __align__(8) uint64_t mma_full[STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tma_full[NR];
+    __shared__ __align__(8) uint64_t raw_empty[NR];
+    __shared__ __align__(8) uint64_t lo_full[NL];
+    __shared__ __align__(8) uint64_t lo_empty[NL];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_slot;
 
@@ -140,11 +85,8 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&tma_full[s], 1);
-            mbar_init(&mma_full[s], kSplitThreads);
-            mbar_init(&empty_bar[s], 1);
-        }
+        for (int s = 0; s < NR; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&raw_empty[s], 1); }
+        for (int s = 0; s < NL; ++s) { mbar_init(&lo_full[s], kSplitThreads / 32); mbar_init(&lo_empty[s], 1); }
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -162,54 +104,47 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     if (warp < 8) {
         // ===================== residual pass: lo = raw - trunc_tf32(raw) =====================
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            mbar_wait(&tma_full[s], (uint32_t)((kb / STAGES) & 1));
-            const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
+            const int sr = kb % NR, sl = kb % NL;
+            mbar_wait(&lo_empty[sl], (uint32_t)(((kb / NL) & 1) ^ 1));      // residual slot drained by the tensor core
+            mbar_wait(&tma_full[sr], (uint32_t)((kb / NR) & 1));            // raw tiles landed
+            const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
+            const uint32_t lo = smem_base + kLoBase + (uint32_t)sl * kRawStage;
 #pragma unroll
-            for (int i = 0; i < (int)(kABytes / 16) / kSplitThreads; ++i) {
-                const uint32_t off = (uint32_t)(tid + i * kSplitThreads) * 16u;
-                float4 v;
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + off));
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + kABytes + off), "f"(resid(v.x)),
-                             "f"(resid(v.y)), "f"(resid(v.z)), "f"(resid(v.w))
-                             : "memory");
-            }
-#pragma unroll
-            for (int i = 0; i < ((int)(kBBytes / 16) + kSplitThreads - 1) / kSplitThreads; ++i) {
+            for (int i = 0; i < (int)(kRawStage / 16 + kSplitThreads - 1) / kSplitThreads; ++i) {
                 const uint32_t q = (uint32_t)(tid + i * kSplitThreads);
-                if (q < kBBytes / 16) {
-                    const uint32_t off = q * 16u;
+                if (q < kRawStage / 16) {
                     float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + 2 * kABytes + off));
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + 2 * kABytes + kBBytes + off),
-                                 "f"(resid(v.x)), "f"(resid(v.y)), "f"(resid(v.z)), "f"(resid(v.w))
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raw + q * 16u));
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + q * 16u), "f"(resid(v.x)), "f"(resid(v.y)),
+                                 "f"(resid(v.z)), "f"(resid(v.w))
                                  : "memory");
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&mma_full[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lo_full[sl]);                        // one arrival per warp
         }
     } else {
         if (warp == 8 && lane == 0) {
             // ===================== TMA producer =====================
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&empty_bar[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
-                const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
+                const int sr = kb % NR;
+                mbar_wait(&raw_empty[sr], (uint32_t)(((kb / NR) & 1) ^ 1));
+                const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
                 const int k0 = kbeg + kb * kBlockK;
-                mbar_expect_tx(&tma_full[s], kABytes + kBBytes);
+                mbar_expect_tx(&tma_full[sr], kRawStage);
                 if (A_MN) {
 #pragma unroll
-                    for (int bi = 0; bi < 4; ++bi) tma_load_3d(st + bi * 4096, mapA, &tma_full[s], m0 + 32 * bi, k0, batch);
+                    for (int bi = 0; bi < 4; ++bi) tma_load_3d(raw + bi * 4096, mapA, &tma_full[sr], m0 + 32 * bi, k0, batch);
                 } else {
-                    tma_load_3d(st, mapA, &tma_full[s], k0, m0, batch);
+                    tma_load_3d(raw, mapA, &tma_full[sr], k0, m0, batch);
                 }
                 if (B_MN) {
 #pragma unroll
                     for (int bi = 0; bi < BN / 32; ++bi)
-                        tma_load_3d(st + 2 * kABytes + bi * 4096, mapB, &tma_full[s], n0 + 32 * bi, k0, batch);
+                        tma_load_3d(raw + kABytes + bi * 4096, mapB, &tma_full[sr], n0 + 32 * bi, k0, batch);
                 } else {
-                    tma_load_3d(st + 2 * kABytes, mapB, &tma_full[s], k0, n0, batch);
+                    tma_load_3d(raw + kABytes, mapB, &tma_full[sr], k0, n0, batch);
                 }
             }
         } else if (warp == 9 && lane == 0) {
@@ -217,14 +152,15 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&mma_full[s], (uint32_t)((kb / STAGES) & 1));
+                const int sr = kb % NR, sl = kb % NL;
+                mbar_wait(&lo_full[sl], (uint32_t)((kb / NL) & 1));          // implies tma_full[sr] (the residual warps waited on it)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
-                const uint64_t a_raw = A_MN ? desc_mnmajor(st) : desc_kmajor(st);
-                const uint64_t a_lo = A_MN ? desc_mnmajor(st + kABytes) : desc_kmajor(st + kABytes);
-                const uint64_t b_raw = B_MN ? desc_mnmajor(st + 2 * kABytes) : desc_kmajor(st + 2 * kABytes);
-                const uint64_t b_lo = B_MN ? desc_mnmajor(st + 2 * kABytes + kBBytes) : desc_kmajor(st + 2 * kABytes + kBBytes);
+                const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
+                const uint32_t lo = smem_base + kLoBase + (uint32_t)sl * kRawStage;
+                const uint64_t a_raw = A_MN ? desc_mnmajor(raw) : desc_kmajor(raw);
+                const uint64_t a_lo = A_MN ? desc_mnmajor(lo) : desc_kmajor(lo);
+                const uint64_t b_raw = B_MN ? desc_mnmajor(raw + kABytes) : desc_kmajor(raw + kABytes);
+                const uint64_t b_lo = B_MN ? desc_mnmajor(lo + kABytes) : desc_kmajor(lo + kABytes);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const uint64_t adv_a = (uint64_t)((A_MN ? kk * 1024 : kk * 32) >> 4);
@@ -234,7 +170,8 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
                     umma_tf32(tmem_d + 3u * BN, a_raw + adv_a, b_lo + adv_b, idesc, 1u);
                     umma_tf32(tmem_d + (uint32_t)(gstep % 3) * BN, a_raw + adv_a, b_raw + adv_b, idesc, gstep >= 3 ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[s]);
+                umma_commit(&raw_empty[sr]);                                 // both slots are free once these MMAs retire
+                umma_commit(&lo_empty[sl]);
             }
             umma_commit(&accum_bar);
         }
@@ -311,8 +248,8 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     }
 }
 
-template <int BN, int STAGES>
-constexpr size_t smem_bytes() { return (size_t)STAGES * (2 * 128 * 128 + 2 * BN * 128) + 1024; }
+template <int BN, int NR, int NL>
+constexpr size_t smem_bytes() { return (size_t)(NR + NL) * (128 * 128 + BN * 128) + 1024; }
 
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -364,29 +301,35 @@ int get_map(const float* ptr, long long inner, long long outer, long long ld, lo
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int NR, int NL>
 int launch_bn(cudaStream_t st, const TmaGroup& grp, bool a_mn, bool b_mn, dim3 grid, double flops, double bytes) {
     ProfScope ps(st, BN <= 64 ? K_TC_GEMM_SKINNY : K_TC_GEMM, flops, bytes);
-    const size_t sm = smem_bytes<BN, STAGES>();
-    if (!a_mn && !b_mn) tma_gemm_kernel<BN, STAGES, false, false><<<grid, kThreads, sm, st>>>(grp);
-    else if (!a_mn && b_mn) tma_gemm_kernel<BN, STAGES, false, true><<<grid, kThreads, sm, st>>>(grp);
-    else if (a_mn && !b_mn) tma_gemm_kernel<BN, STAGES, true, false><<<grid, kThreads, sm, st>>>(grp);
-    else tma_gemm_kernel<BN, STAGES, true, true><<<grid, kThreads, sm, st>>>(grp);
+    const size_t sm = smem_bytes<BN, NR, NL>();
+    if (!a_mn && !b_mn) tma_gemm_kernel<BN, NR, NL, false, false><<<grid, kThreads, sm, st>>>(grp);
+    else if (!a_mn && b_mn) tma_gemm_kernel<BN, NR, NL, false, true><<<grid, kThreads, sm, st>>>(grp);
+    else if (a_mn && !b_mn) tma_gemm_kernel<BN, NR, NL, true, false><<<grid, kThreads, sm, st>>>(grp);
+    else tma_gemm_kernel<BN, NR, NL, true, true><<<grid, kThreads, sm, st>>>(grp);
     NATS_LAUNCH_OK();
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int NR, int NL>
 int set_attrs() {
-    const int sm = (int)smem_bytes<BN, STAGES>();
-    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, STAGES, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, STAGES, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, STAGES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, STAGES, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    const int sm = (int)smem_bytes<BN, NR, NL>();
+    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, NR, NL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, NR, NL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, NR, NL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, NR, NL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     return 0;
 }
 
 }  // namespace
+
+int tma_map_3d(const float* ptr, long long inner, long long outer, long long ld, long long batch, long long bstride,
+               int box_outer, bool mn_major, CUtensorMap* out) {
+    return get_map(ptr, inner, outer, ld, batch, bstride, box_outer, mn_major, out);
+}
+bool tma_available() { return g_encode != nullptr; }
 
 int tma_gemm_setup() {
     void* fn = nullptr;
@@ -397,9 +340,9 @@ int tma_gemm_setup() {
         return 1;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    NATS_TRY((set_attrs<32, 4>()));
-    NATS_TRY((set_attrs<64, 4>()));
-    NATS_TRY((set_attrs<128, 3>()));
+    NATS_TRY((set_attrs<32, 8, 2>()));
+    NATS_TRY((set_attrs<64, 6, 2>()));
+    NATS_TRY((set_attrs<128, 5, 2>()));
     return 0;
 }
 
@@ -466,9 +409,9 @@ int tma_gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool t
     for (int i = count; i < kMaxGroup; ++i) grp.zstart[i + 1] = z;
     if (ga == 0 || gb == 0 || z == 0) return 0;
     dim3 grid(ga, gb, z);
-    if (BN == 32) return launch_bn<32, 4>(st, grp, a_mn, b_mn, grid, flops, bytes);
-    if (BN == 64) return launch_bn<64, 4>(st, grp, a_mn, b_mn, grid, flops, bytes);
-    return launch_bn<128, 3>(st, grp, a_mn, b_mn, grid, flops, bytes);
+    if (BN == 32) return launch_bn<32, 8, 2>(st, grp, a_mn, b_mn, grid, flops, bytes);
+    if (BN == 64) return launch_bn<64, 6, 2>(st, grp, a_mn, b_mn, grid, flops, bytes);
+    return launch_bn<128, 5, 2>(st, grp, a_mn, b_mn, grid, flops, bytes);
 }
 
 }  // namespace nats

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm.cuh"
+#include "ops.cuh"
 
 namespace nats {
 
@@ -142,6 +143,9 @@ struct TrainWS {
     float* gemm_scratch; // split-K slabs for gemm_auto
     int64_t gemm_scratch_floats;
     float* red_scratch;  // column-sum scratch: 64 * max(V, 3D, C) floats
+    float* step_slab;    // split-K exchange of the fused recurrent-step kernels
+    int* step_counters;  // their per-tile tickets (zeroed before every recurrence)
+    int64_t step_counter_ints;
     int64_t bytes;
 };
 
@@ -183,6 +187,9 @@ inline TrainWS carve_train(const nats_dims_t& d, int Tx, int Ty, int B, void* ba
     w.gemm_scratch_floats = 8LL << 20;
     w.gemm_scratch = c.f(w.gemm_scratch_floats);
     { int64_t mx = V; if (3 * D > mx) mx = 3 * D; w.red_scratch = c.f(64 * mx); }
+    w.step_slab = c.f(gru_step_slab_floats(B, (int)D));
+    w.step_counter_ints = gru_step_counter_ints((int)D);
+    w.step_counters = c.take<int>(w.step_counter_ints);
     w.bytes = round_up64(c.off, 256);
     return w;
 }
@@ -209,6 +216,9 @@ struct SamplerWS {
     float* logits;      // [n, V]
     float* gemm_scratch;
     int64_t gemm_scratch_floats;
+    float* step_slab;
+    int* step_counters;
+    int64_t step_counter_ints;
     int64_t bytes;
 };
 
@@ -229,6 +239,9 @@ inline SamplerWS carve_sampler(const nats_dims_t& d, int Tx, int n, void* base) 
     w.h1 = c.f(n * D); w.ps = c.f(n * A); w.craw = c.f(n * C); w.L = c.f(n * W); w.logits = c.f(n * V);
     w.gemm_scratch_floats = 4LL << 20;
     w.gemm_scratch = c.f(w.gemm_scratch_floats);
+    w.step_slab = c.f(gru_step_slab_floats(n, (int)D));
+    w.step_counter_ints = gru_step_counter_ints((int)D);
+    w.step_counters = c.take<int>(w.step_counter_ints);
     w.bytes = round_up64(c.off, 256);
     return w;
 }
