@@ -28,6 +28,7 @@ import warnings
 import numpy
 
 from . import _lib
+from . import parallel
 from ._lib import Dims, NatsB200Error
 from .data_iterator import TextIterator
 
@@ -383,11 +384,7 @@ class ModelGraph(object):
         torch = self.engine.torch
         self.grads = torch.zeros(tparams.total + _lib.GRAD_TAIL, dtype=torch.float32, device=self.engine.device)
         self.stats = torch.zeros(8, dtype=torch.float32, device=self.engine.device)
-        self.world = 1
-        self.rank = 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world = torch.distributed.get_world_size()
-            self.rank = torch.distributed.get_rank()
+        self.rank, self.world = parallel.world()
 
     # -- reference idiom: cost = cost.mean() (nats.py:1323)
     def mean(self):
@@ -471,7 +468,7 @@ class ModelGraph(object):
         p = self.plan(x.shape[0], y.shape[0], x.shape[1])
         p.stage(x, x_mask, y, y_mask)
         B = x.shape[1]
-        scale = 1.0 / (B * self.world)        # d mean(cost) over the GLOBAL batch (nats.py:1323)
+        scale = parallel.grad_scale(B, self.world)   # d mean(cost) over the GLOBAL batch (nats.py:1323)
 
         def fwd_bwd():
             self.enqueue_fwd(p)
@@ -485,7 +482,7 @@ class ModelGraph(object):
             self._run(p, 'graph_step', lambda: (fwd_bwd(), post()))
         else:
             self._run(p, 'graph_fb', fwd_bwd)
-            torch.distributed.all_reduce(self.grads)          # ONE collective: gradients + cost tail
+            parallel.allreduce_flat(self.grads)               # ONE collective: gradients + cost tail
             self._run(p, 'graph_post', post)
         p.uses += 1
         cost = float(self.grads[self.tparams.total].item())   # device->host read of the step result

@@ -1,0 +1,33 @@
+"""Data parallelism of the hot path: the batch dimension shards across ranks (one process per GPU),
+parameters and optimiser state are replicated, and ONE all-reduce per step sums the flat gradient buffer -- whose
+tail slot carries the cost, so no second collective is needed.  Every rank scales its local gradient by
+1 / (global batch), hence the sum equals d mean(cost) of nats.py:1323; clipping (nats.py:1344-1353) and the
+optimiser then see identical buffers on all ranks.  Backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+
+
+def world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def grad_scale(local_batch, world_size, global_batch=None):
+    """weight of every local sample's cost so that the all-reduced sum is the mean over the global batch"""
+    return 1.0 / float(global_batch if global_batch is not None else local_batch * world_size)
+
+
+def shard(seqs_x, seqs_y, rank, world_size):
+    """contiguous, equal shards of a global batch of sentence pairs (the last ranks may get one pair less)"""
+    n = len(seqs_x)
+    per = (n + world_size - 1) // world_size
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    return seqs_x[lo:hi], seqs_y[lo:hi]
+
+
+def allreduce_flat(flat):
+    """in-place SUM of the flat gradient buffer (+ cost tail) over all ranks; no-op for a single process"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
