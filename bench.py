@@ -103,8 +103,48 @@ class ClockSampler(object):
         return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def best_blas_threads():
+    """OpenBLAS with every host thread (128 on the B200 boxes) is pathologically slow on the skinny products of the
+    recurrence; pick the thread count that is fastest on representative shapes so the CPU baseline is a fair one."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        return None, os.cpu_count()
+    ncpu = os.cpu_count() or 1
+    rng = np.random.RandomState(0)
+    a1, b1 = rng.randn(32, 1000).astype('float32'), rng.randn(1000, 3000).astype('float32')
+    a2, b2 = rng.randn(960, 100).astype('float32'), rng.randn(100, 30000).astype('float32')
+    best = (None, 1e30)
+    for t in sorted(set([4, 8, 16, 32, 64, ncpu])):
+        if t > ncpu:
+            continue
+        with threadpool_limits(limits=t):
+            a1 @ b1; a2 @ b2
+            t0 = time.perf_counter()
+            for _ in range(20):
+                a1 @ b1
+            for _ in range(2):
+                a2 @ b2
+            dt = time.perf_counter() - t0
+        if dt < best[1]:
+            best = (t, dt)
+    return threadpool_limits, best[0]
+
+
 def cpu_reference_run(w, steps, warmup, sample_B=8):
     """Times the float32 CPU restatement on a bounded sample of the workload; returns tokens/s and details."""
+    limiter, nthreads = best_blas_threads()
+    if limiter is not None:
+        with limiter(limits=nthreads):
+            r = _cpu_reference_run(w, steps, warmup, sample_B)
+    else:
+        r = _cpu_reference_run(w, steps, warmup, sample_B)
+    r['cores'] = nthreads
+    r['sample'] += '; BLAS threads chosen by calibration out of %d host threads' % (os.cpu_count() or 1)
+    return r
+
+
+def _cpu_reference_run(w, steps, warmup, sample_B=8):
     from oracle import nats_oracle as O
     opts = options_of(w)
     np.random.seed(1234)
@@ -164,6 +204,7 @@ def main():
         print(json.dumps(line))
         return 0
 
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep NCCL's banner off the one-JSON-line stdout
     import torch
     if world > 1:
         torch.cuda.set_device(local)
