@@ -51,6 +51,12 @@ void prof_end(cudaStream_t st) {
 }
 }  // namespace nats
 
+namespace nats {
+static int g_pdl = 1;
+int pdl_enabled() { return g_pdl; }
+void pdl_set(int on) { g_pdl = on; }
+}  // namespace nats
+
 using namespace nats;
 
 namespace {
@@ -90,6 +96,7 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     if (r == 0) r = tc_gemm_setup();
     if (r == 0) r = tma_gemm_setup();
     if (r == 0) r = gru_step_setup();
+    pdl_set(getenv("NATS_PDL") ? atoi(getenv("NATS_PDL")) : 1);
     gru_step_enable(getenv("NATS_FUSED_STEP") ? atoi(getenv("NATS_FUSED_STEP")) : 0);
     gemm_set_tensor_cores(getenv("NATS_TC") ? atoi(getenv("NATS_TC")) : 2);
     if (r != 0) { cudaFree(c->dev_scratch); delete c; return r; }

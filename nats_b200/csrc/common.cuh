@@ -6,6 +6,8 @@
 #include <string.h>
 #include <math.h>
 
+#include <utility>
+
 #include "../../include/nats_b200.h"
 #include "prof.cuh"
 
@@ -58,6 +60,22 @@ constexpr int kCtxScratchFloats = 16384;
 
 namespace nats {
 
+int pdl_enabled();
+void pdl_set(int on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up64(int64_t a, int64_t b) { return cdiv64(a, b) * b; }
@@ -101,6 +119,13 @@ __device__ __forceinline__ float block_max(float v, float* red) {
     float r = (lane < nw) ? red[lane] : -INFINITY;
     return warp_max(r);
 }
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A kernel launched through launch_pdl() may start while its predecessor in the stream is still running: it calls
+// pdl_trigger() as early as possible (lets ITS dependents launch) and pdl_wait() before the first access to memory that
+// a predecessor may have written or may still read.  Kernels without the attribute keep the ordinary stream order.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // streaming (read-once) 128-bit load that does not pollute L1
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {

@@ -105,6 +105,8 @@ sgemm_kernel(const __grid_constant__ GemmGroup grp) {
     const int split = z % P.splitk, batch = z / P.splitk;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     if (m0 >= P.M || n0 >= P.N) return;
+    pdl_trigger();
+    pdl_wait();
 
     const int kbeg = split * P.kchunk;
     const int kend = min(P.K, kbeg + P.kchunk);
@@ -231,17 +233,20 @@ int launch_cfg(cudaStream_t st, const GemmGroup& grp, bool ta, bool tb) {
         }
     const int cfg_id = (BM == 128) ? 0 : (BM == 64 ? 1 : 2);
     ProfScope ps(st, K_GEMM_BASE + cfg_id * 4 + (ta ? 2 : 0) + (tb ? 1 : 0), flops, bytes);
-    if (!ta && !tb) sgemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, block, 0, st>>>(grp);
-    else if (!ta && tb) sgemm_kernel<BM, BN, BK, TM, TN, false, true><<<grid, block, 0, st>>>(grp);
-    else if (ta && !tb) sgemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, block, 0, st>>>(grp);
-    else sgemm_kernel<BM, BN, BK, TM, TN, true, true><<<grid, block, 0, st>>>(grp);
-    NATS_LAUNCH_OK();
+    cudaError_t le;
+    if (!ta && !tb) le = launch_pdl(sgemm_kernel<BM, BN, BK, TM, TN, false, false>, grid, block, 0, st, grp);
+    else if (!ta && tb) le = launch_pdl(sgemm_kernel<BM, BN, BK, TM, TN, false, true>, grid, block, 0, st, grp);
+    else if (ta && !tb) le = launch_pdl(sgemm_kernel<BM, BN, BK, TM, TN, true, false>, grid, block, 0, st, grp);
+    else le = launch_pdl(sgemm_kernel<BM, BN, BK, TM, TN, true, true>, grid, block, 0, st, grp);
+    NATS_CUDA_OK(le);
     return 0;
 }
 
 __global__ void reduce_splits_kernel(const float* __restrict__ part, int nsplit, long long strideP, int M, int N,
                                      int ldp, float* __restrict__ out, int ldo, const float* __restrict__ bias,
                                      int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)M * N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -266,7 +271,7 @@ static bool tc_eligible(const GemmProblem* probs, int count) {
     if (!g_use_tc) return false;
     for (int i = 0; i < count; ++i) {
         const int big = probs[i].M > probs[i].N ? probs[i].M : probs[i].N;
-        if (big < 128 || probs[i].K < 32) return false;
+        if (big < 64 || probs[i].K < 32) return false;
     }
     return true;
 }
@@ -340,8 +345,8 @@ int reduce_splits(cudaStream_t st, const float* part, int nsplit, long long stri
     if (gl > 148LL * 16) gl = 148LL * 16;
     const int grid = (int)gl;
     ProfScope ps(st, K_REDUCE_SPLITS, 0.0, 4.0 * total * (nsplit + 1));
-    reduce_splits_kernel<<<grid, block, 0, st>>>(part, nsplit, strideP, M, N, ldp, out, ldo, bias, accumulate);
-    NATS_LAUNCH_OK();
+    NATS_CUDA_OK(launch_pdl(reduce_splits_kernel, dim3(grid), dim3(block), 0, st, part, nsplit, strideP, M, N, ldp, out, ldo, bias,
+                            accumulate));
     return 0;
 }
 

@@ -25,6 +25,7 @@ struct GemmProblem {
     int kchunk;            // K range per split (multiple of 16)
     long long strideP;     // distance between split slabs of C
     int accumulate;        // C += result (only with splitk == 1)
+    int a_static, b_static; // operand is constant within the step (a weight matrix): PDL kernels may prefetch it early
 };
 
 constexpr int kGemmMaxGroup = 4;

@@ -85,6 +85,7 @@ int train_decoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
             gemm_set_split(q[0], SA, spD);
             q[1] = gemm_problem(w.dG1x + r3, D3, params + o.W1cat, D3, w.part_a, C, B, C, D3);
             gemm_set_split(q[1], SB, spC);
+            q[0].b_static = q[1].b_static = 1;
             NATS_TRY(gemm_launch(st, q, 2, false, true, cfg));
         }
         {   // distraction + attention backward (nats.py:527-546, 569-570)
@@ -111,6 +112,7 @@ int train_decoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
         }
         {   // d h1 += d ps . W_att^T  (nats.py:527)
             GemmProblem q = gemm_problem(w.dps + rA, A, params + o.W_att, A, w.part_d, D, B, D, A);
+            q.b_static = 1;
             NATS_TRY(gemm_launch(st, &q, 1, false, true, cfg));
         }
         {   // GRU_2 backward (nats.py:505-518)
@@ -128,6 +130,7 @@ int train_decoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
         {   // d h_{t-1} through the GRU_2 recurrent product
             GemmProblem q = gemm_problem(w.dG2 + r3, D3, params + o.dec.Ucat, D3, w.part_c, D, B, D, D3);
             gemm_set_split(q, S4, spD);
+            q.b_static = 1;
             NATS_TRY(gemm_launch(st, &q, 1, false, true, cfg));
         }
     }
@@ -237,6 +240,7 @@ int train_encoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
                 q[dir] = gemm_problem(w.dGe[dir] + (long long)pos * B * D3, D3, params + o.enc[dir].Ucat, D3,
                                       w.part_a + (long long)dir * B * D, D, B, D, D3);
                 gemm_set_split(q[dir], S, strideP);
+                q[dir].b_static = 1;
             }
             NATS_TRY(gemm_launch(st, q, 2, false, true, cfg));
         }

@@ -58,6 +58,7 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
                                 e.part_a + (long long)n * D3, D3, n, D3, D);
             gemm_set_split(q[0], S, strideP);
             gemm_set_split(q[1], S, strideP);
+            q[0].b_static = q[1].b_static = 1;
             NATS_TRY(gemm_launch(st, q, 2, false, false, cfg));
         }
         GateFwd g[2];
@@ -116,6 +117,7 @@ int decoder_step_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t
     } else {   // GRU_2 recurrent product (nats.py:505, 512)
         GemmProblem q = gemm_problem(s.h_prev, D, params + o.dec.Ucat, D3, s.part_b, D3, n, D3, D);
         gemm_set_split(q, S1, sp3);
+        q.b_static = 1;
         NATS_TRY(gemm_launch(st, &q, 1, false, false, cfg));
         GateFwd g;
         memset(&g, 0, sizeof(g));
@@ -133,6 +135,7 @@ int decoder_step_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t
         gemm_set_split(q[0], S1, sp3);
         q[1] = gemm_problem(s.h1, D, params + o.W_att, A, s.part_d, A, n, A, D);
         gemm_set_split(q[1], S1, (long long)n * A);
+        q[0].b_static = q[1].b_static = 1;
         NATS_TRY(gemm_launch(st, q, 2, false, false, cfg));
     }
     {
@@ -155,6 +158,7 @@ int decoder_step_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t
     {   // GRU_1 (nats.py:551-565)
         GemmProblem q = gemm_problem(s.ctx_out, C, params + o.W1cat, D3, s.part_a, D3, n, D3, C);
         gemm_set_split(q, S2, sp3);
+        q.b_static = 1;
         NATS_TRY(gemm_launch(st, &q, 1, false, false, cfg));
         GateFwd g;
         memset(&g, 0, sizeof(g));

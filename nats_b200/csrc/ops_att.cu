@@ -55,6 +55,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ------------------------------------------------------------------ forward: energies
 __global__ void __launch_bounds__(kAttThreads) att_scores_kernel(const __grid_constant__ AttFwd a) {
     extern __shared__ float sm[];
+    pdl_trigger();
+    pdl_wait();
     float* s_ps = sm;
     float* s_dw = sm + a.A;
     float* s_ua = sm + 2 * a.A;
@@ -110,15 +112,19 @@ __global__ void __launch_bounds__(kAttThreads) att_context_kernel(const __grid_c
                      ccb + (long long)(t0 + lane) * a.cc_tstride, (uint32_t)(len * 4), &bars[stage]);
     };
 
+    pdl_trigger();
     if (BULK) {
         if (tid == 0) {
             for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
             fence_barrier_init();
         }
         __syncthreads();
+        // the encoder context cc is not written by any kernel of the decoder scan: its first tiles are requested
+        // before the predecessor (the energies kernel) has finished
         if (tid < 32)
             for (int blk = 0; blk < kStages && blk < nblk; ++blk) issue(blk);
     }
+    pdl_wait();
 
     // masked softmax over the source positions (nats.py:537-540); max taken over valid positions only
     float lmax = -INFINITY;
@@ -195,6 +201,8 @@ __global__ void __launch_bounds__(kAttThreads) att_context_kernel(const __grid_c
 
 // ------------------------------------------------------------------ backward kernels
 __global__ void att_bwd_ctx_kernel(const __grid_constant__ AttBwd a) {
+    pdl_trigger();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.B * a.C) return;
     const int b = idx / a.C, c = idx - b * a.C;
@@ -212,6 +220,8 @@ __global__ void att_bwd_ctx_kernel(const __grid_constant__ AttBwd a) {
 
 __global__ void __launch_bounds__(kAttThreads) att_bwd_dalpha_kernel(const __grid_constant__ AttBwd a) {
     extern __shared__ __align__(16) float s_dcraw[];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < a.C; i += blockDim.x) s_dcraw[i] = a.dcraw[(long long)b * a.C + i];
     __syncthreads();
@@ -248,6 +258,8 @@ constexpr int kMaxAk = 8;   // A <= 256
 
 __global__ void __launch_bounds__(kSoftThreads) att_bwd_softmax_kernel(const __grid_constant__ AttBwd a) {
     extern __shared__ float sm[];
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32];
     const int A = a.A, Tx = a.Tx, b = blockIdx.x, tid = threadIdx.x;
     float* s_de = sm;                 // [Tx]
@@ -363,8 +375,7 @@ int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
     {
         dim3 grid(cdiv(a.Tx, kRowsPerCta), a.n);
         ProfScope ps(st, K_ATT_SCORES, 0.0, 4.0 * a.Tx * (a.pctx_bstride == 0 ? 1 : a.n) * a.A);
-        att_scores_kernel<<<grid, kAttThreads, 3 * a.A * sizeof(float), st>>>(a);
-        NATS_LAUNCH_OK();
+        NATS_CUDA_OK(launch_pdl(att_scores_kernel, grid, dim3(kAttThreads), 3 * a.A * sizeof(float), st, a));
     }
     // column slices: aim at >= 2 CTAs per SM
     int target = cdiv(2 * ctx->num_sms, a.n);
@@ -384,9 +395,8 @@ int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
     dim3 grid(nslices, a.n);
     ProfScope ps(st, K_ATT_CONTEXT, 2.0 * a.Tx * a.n * a.C,
                  4.0 * ((double)a.Tx * (a.cc_bstride == 0 ? 1 : a.n) * a.C + 3.0 * a.n * a.Tx + 4.0 * a.n * a.C));
-    if (bulk) att_context_kernel<true><<<grid, kAttThreads, smem, st>>>(a, slice, slice_pad);
-    else att_context_kernel<false><<<grid, kAttThreads, smem, st>>>(a, slice, slice_pad);
-    NATS_LAUNCH_OK();
+    if (bulk) NATS_CUDA_OK(launch_pdl(att_context_kernel<true>, grid, dim3(kAttThreads), smem, st, a, slice, slice_pad));
+    else NATS_CUDA_OK(launch_pdl(att_context_kernel<false>, grid, dim3(kAttThreads), smem, st, a, slice, slice_pad));
     return 0;
 }
 
@@ -394,21 +404,18 @@ int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a) {
     NATS_REQUIRE(a.A <= 32 * kMaxAk, "dim_att > 256 not supported by the attention backward kernel");
     {
         ProfScope ps(st, K_ATT_BWD_CTX);
-        att_bwd_ctx_kernel<<<cdiv(a.B * a.C, 256), 256, 0, st>>>(a);
-        NATS_LAUNCH_OK();
+        NATS_CUDA_OK(launch_pdl(att_bwd_ctx_kernel, dim3(cdiv(a.B * a.C, 256)), dim3(256), 0, st, a));
     }
     {
         dim3 grid(cdiv(a.Tx, kRowsPerCta), a.B);
         ProfScope ps(st, K_ATT_BWD_DALPHA, 2.0 * a.Tx * a.B * a.C, 4.0 * ((double)a.Tx * a.B * a.C + 2.0 * a.B * a.Tx));
-        att_bwd_dalpha_kernel<<<grid, kAttThreads, (size_t)a.C * sizeof(float), st>>>(a);
-        NATS_LAUNCH_OK();
+        NATS_CUDA_OK(launch_pdl(att_bwd_dalpha_kernel, grid, dim3(kAttThreads), (size_t)a.C * sizeof(float), st, a));
     }
     {
         const size_t smem = ((size_t)2 * a.Tx + 3 * a.A + (size_t)kSoftWarps * 3 * a.A) * sizeof(float);
         NATS_REQUIRE(smem <= (size_t)g_att_dyn_limit, "source too long for the attention backward kernel");
         ProfScope ps(st, K_ATT_BWD_SOFTMAX, 0.0, 12.0 * a.Tx * a.B * a.A);
-        att_bwd_softmax_kernel<<<a.B, kSoftThreads, smem, st>>>(a);
-        NATS_LAUNCH_OK();
+        NATS_CUDA_OK(launch_pdl(att_bwd_softmax_kernel, dim3(a.B), dim3(kSoftThreads), smem, st, a));
     }
     return 0;
 }

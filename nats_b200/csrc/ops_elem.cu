@@ -39,6 +39,8 @@ struct GateBwdPack { GateBwd g[2]; };
 
 template <int MODE>
 __global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, int B, int D) {
+    pdl_trigger();
+    pdl_wait();
     const GateFwd& a = pack.g[blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * D) return;
@@ -78,6 +80,8 @@ __global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, i
 }
 
 __global__ void gru_gates_bwd_kernel(const __grid_constant__ GateBwdPack pack, int B, int D) {
+    pdl_trigger();
+    pdl_wait();
     const GateBwd& a = pack.g[blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * D) return;
@@ -225,9 +229,8 @@ int gru_gates_fwd(cudaStream_t st, const GateFwd* groups, int ngroups, int B, in
     for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
     dim3 grid(cdiv(B * D, 256), ngroups);
     ProfScope ps(st, K_GATES_FWD);
-    if (mode == 0) gru_gates_fwd_kernel<0><<<grid, 256, 0, st>>>(pack, B, D);
-    else gru_gates_fwd_kernel<1><<<grid, 256, 0, st>>>(pack, B, D);
-    NATS_LAUNCH_OK();
+    if (mode == 0) NATS_CUDA_OK(launch_pdl(gru_gates_fwd_kernel<0>, grid, dim3(256), 0, st, pack, B, D));
+    else NATS_CUDA_OK(launch_pdl(gru_gates_fwd_kernel<1>, grid, dim3(256), 0, st, pack, B, D));
     return 0;
 }
 int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, int D) {
@@ -237,8 +240,7 @@ int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, in
     for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
     dim3 grid(cdiv(B * D, 256), ngroups);
     ProfScope ps(st, K_GATES_BWD);
-    gru_gates_bwd_kernel<<<grid, 256, 0, st>>>(pack, B, D);
-    NATS_LAUNCH_OK();
+    NATS_CUDA_OK(launch_pdl(gru_gates_bwd_kernel, grid, dim3(256), 0, st, pack, B, D));
     return 0;
 }
 

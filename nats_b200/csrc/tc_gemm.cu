@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
+    pdl_trigger();
+    pdl_wait();
 
     if (warp < 8) {
         // ===================== loaders =====================
@@ -368,8 +370,7 @@ int tc_launch(cudaStream_t st, const TcGroup& grp) {
     }
     ProfScope ps(st, BN <= 64 ? K_TC_GEMM_SKINNY : K_TC_GEMM, flops, bytes);
     dim3 grid(ga, gb, gz);
-    tc_gemm_kernel<BN, STAGES><<<grid, kTcThreads, tc_smem_bytes<BN, STAGES>(), st>>>(grp);
-    NATS_LAUNCH_OK();
+    NATS_CUDA_OK(launch_pdl(tc_gemm_kernel<BN, STAGES>, grid, dim3(kTcThreads), tc_smem_bytes<BN, STAGES>(), st, grp));
     return 0;
 }
 

@@ -40,6 +40,7 @@ struct TmaProblem {
     long long strideP;
     int accumulate;
     int bias_on_a;
+    int a_static;        // the 128-row operand is constant within the step (weights): may be prefetched before pdl_wait
 };
 struct alignas(64) TmaGroup {
     CUtensorMap mapA[kMaxGroup];
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
+    pdl_trigger();                      // dependents may launch now (they block in their own pdl_wait)
 
     if (warp < 8) {
         // ===================== residual pass: lo = raw - trunc_tf32(raw) =====================
@@ -127,11 +129,38 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     } else {
         if (warp == 8 && lane == 0) {
             // ===================== TMA producer =====================
+            // With PDL the predecessor kernel may still be running: operands it produces must not be read before
+            // pdl_wait().  When `a_static` (the 128-row operand is a weight matrix, constant within the step) its
+            // tiles for the first ring fill are prefetched BEFORE the wait.
+            const int npre = P.a_static ? min(nkb, NR) : 0;
+            for (int kb = 0; kb < npre; ++kb) {
+                const uint32_t raw = smem_base + (uint32_t)kb * kRawStage;
+                const int k0 = kbeg + kb * kBlockK;
+                mbar_expect_tx_only(&tma_full[kb], kABytes);
+                if (A_MN) {
+#pragma unroll
+                    for (int bi = 0; bi < 4; ++bi) tma_load_3d(raw + bi * 4096, mapA, &tma_full[kb], m0 + 32 * bi, k0, batch);
+                } else {
+                    tma_load_3d(raw, mapA, &tma_full[kb], k0, m0, batch);
+                }
+            }
+            pdl_wait();
             for (int kb = 0; kb < nkb; ++kb) {
                 const int sr = kb % NR;
                 mbar_wait(&raw_empty[sr], (uint32_t)(((kb / NR) & 1) ^ 1));
                 const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
                 const int k0 = kbeg + kb * kBlockK;
+                if (kb < npre) {                  // A already in flight: only B left for this stage
+                    mbar_expect_tx(&tma_full[sr], kBBytes);
+                    if (B_MN) {
+#pragma unroll
+                        for (int bi = 0; bi < BN / 32; ++bi)
+                            tma_load_3d(raw + kABytes + bi * 4096, mapB, &tma_full[sr], n0 + 32 * bi, k0, batch);
+                    } else {
+                        tma_load_3d(raw + kABytes, mapB, &tma_full[sr], k0, n0, batch);
+                    }
+                    continue;
+                }
                 mbar_expect_tx(&tma_full[sr], kRawStage);
                 if (A_MN) {
 #pragma unroll
@@ -185,6 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
             mbar_wait(&accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        pdl_wait();                     // C may still be read (or accumulated into) by the predecessor
         const float bias_a = (add_bias && P.bias_on_a && i < P.Ma) ? __ldg(P.bias + i) : 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -305,11 +335,12 @@ template <int BN, int NR, int NL>
 int launch_bn(cudaStream_t st, const TmaGroup& grp, bool a_mn, bool b_mn, dim3 grid, double flops, double bytes) {
     ProfScope ps(st, BN <= 64 ? K_TC_GEMM_SKINNY : K_TC_GEMM, flops, bytes);
     const size_t sm = smem_bytes<BN, NR, NL>();
-    if (!a_mn && !b_mn) tma_gemm_kernel<BN, NR, NL, false, false><<<grid, kThreads, sm, st>>>(grp);
-    else if (!a_mn && b_mn) tma_gemm_kernel<BN, NR, NL, false, true><<<grid, kThreads, sm, st>>>(grp);
-    else if (a_mn && !b_mn) tma_gemm_kernel<BN, NR, NL, true, false><<<grid, kThreads, sm, st>>>(grp);
-    else tma_gemm_kernel<BN, NR, NL, true, true><<<grid, kThreads, sm, st>>>(grp);
-    NATS_LAUNCH_OK();
+    cudaError_t le;
+    if (!a_mn && !b_mn) le = launch_pdl(tma_gemm_kernel<BN, NR, NL, false, false>, grid, dim3(kThreads), sm, st, grp);
+    else if (!a_mn && b_mn) le = launch_pdl(tma_gemm_kernel<BN, NR, NL, false, true>, grid, dim3(kThreads), sm, st, grp);
+    else if (a_mn && !b_mn) le = launch_pdl(tma_gemm_kernel<BN, NR, NL, true, false>, grid, dim3(kThreads), sm, st, grp);
+    else le = launch_pdl(tma_gemm_kernel<BN, NR, NL, true, true>, grid, dim3(kThreads), sm, st, grp);
+    NATS_CUDA_OK(le);
     return 0;
 }
 
@@ -398,6 +429,7 @@ int tma_gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool t
         if (q.splitk > 1) t.kchunk = ((cdiv(q.K, q.splitk) + 31) / 32) * 32;
         if (t.kchunk <= 0) t.kchunk = 32;
         t.strideP = q.strideP; t.accumulate = q.accumulate;
+        t.a_static = swapped ? q.b_static : q.a_static;
         grp.zstart[i] = z;
         z += q.batch * q.splitk;
         ga = max(ga, cdiv(t.Ma, 128));

@@ -36,3 +36,26 @@ if __name__ == '__main__':
                 us = bench(path, M, N, K, ta, tb, sk)
                 fl = 2.0 * M * N * K
                 print('%-24s path %d splitk %2d  %9.2f us  %7.1f TFLOP/s  weights %.1f GB/s' % (name, path, sk, us, fl / us / 1e6, 4.0 * N * K / us / 1e3))
+
+
+def bench_graph(path, M, N, K, ta, tb, splitk, chain=100, reps=20):
+    """the same launch `chain` times inside one CUDA graph (dependent chain on one stream)"""
+    lda = M if ta else K; ldb = K if tb else N
+    A = torch.randn((K if ta else M, lda), device='cuda'); B = torch.randn((N if tb else K, ldb), device='cuda')
+    C = torch.zeros((max(splitk, 1), M, N), device='cuda')
+    def run():
+        rc = eng.lib.nats_debug_gemm(eng.ctx, eng.stream(), path, ta, tb, M, N, K, ctypes.c_void_p(A.data_ptr()), lda,
+                                     ctypes.c_void_p(B.data_ptr()), ldb, ctypes.c_void_p(C.data_ptr()), N,
+                                     ctypes.c_void_p(0), 0, splitk, 1, 0, 0, 0)
+        _lib.check(rc)
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(chain): run()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * chain)
