@@ -31,7 +31,7 @@ const char* kNames[K_COUNT] = {
     "gemm_mid_tt", "gemm_smallm_nn", "gemm_smallm_nt", "gemm_smallm_tn", "gemm_smallm_tt", "gru_gates_fwd",
     "gru_gates_bwd", "att_scores", "att_context", "att_bwd_ctx", "att_bwd_dalpha", "att_bwd_softmax", "nll_rows",
     "dlogits", "softmax_sample", "colsum", "reduce_splits", "embedding", "elementwise", "optimizer", "beam",
-    "memset", "tc_gemm_3xtf32", "tc_gemm_3xtf32_skinny", "gru_step_fwd_fused", "gru_step_bwd_fused"};
+    "memset", "tc_gemm_3xtf32", "tc_gemm_3xtf32_skinny", "gru_step_fwd_fused", "gru_step_bwd_fused", "enc_persistent_fwd", "enc_persistent_bwd"};
 }  // namespace
 const char* kclass_name(int cls) { return (cls >= 0 && cls < K_COUNT) ? kNames[cls] : "?"; }
 bool prof_enabled() { return g_prof.on; }
@@ -96,6 +96,8 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     if (r == 0) r = tc_gemm_setup();
     if (r == 0) r = tma_gemm_setup();
     if (r == 0) r = gru_step_setup();
+    if (r == 0) r = enc_persistent_setup(c);
+    enc_persistent_enable(getenv("NATS_PERSISTENT") ? atoi(getenv("NATS_PERSISTENT")) : 0);
     pdl_set(getenv("NATS_PDL") ? atoi(getenv("NATS_PDL")) : 1);
     gru_step_enable(getenv("NATS_FUSED_STEP") ? atoi(getenv("NATS_FUSED_STEP")) : 0);
     gemm_set_tensor_cores(getenv("NATS_TC") ? atoi(getenv("NATS_TC")) : 2);
@@ -310,6 +312,7 @@ const float* nats_train_ws_view(const nats_dims_t* dims, int Tx, int Ty, int B, 
     if (!strcmp(name, "dec_alpha")) return w.d_alpha;
     if (!strcmp(name, "pctx")) return w.pctx;
     if (!strcmp(name, "logits")) return w.logits;
+    if (!strcmp(name, "step_counters")) return reinterpret_cast<const float*>(w.step_counters);
     return nullptr;
 }
 

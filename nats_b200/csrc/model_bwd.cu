@@ -107,6 +107,7 @@ int train_decoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
             a.dps = w.dps + rA;
             a.dpctx = w.dpctx;
             a.gatt_part = w.gatt_part;
+            a.dot_part = w.att_dot_part; a.soft_part = w.att_soft_part;
             a.Tx = Tx; a.B = B; a.A = A; a.C = C;
             NATS_TRY(attention_bwd(ctx, st, a));
         }
@@ -193,8 +194,22 @@ int train_encoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
     const int S = gemm_pick_split(ctx, B, D, D3, 2);
     const long long strideP = 2LL * B * D;
     const bool fused = gru_step_eligible(B, D);
-    if (fused) NATS_CUDA_OK(memset_async(st, w.step_counters, 0, (size_t)w.step_counter_ints * sizeof(int)));
-    for (int s = Tx - 1; s >= 0; --s) {
+    const bool persistent = enc_persistent_eligible(ctx, B, D);
+    if (persistent) {
+        EncPersistBwdArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        for (int dir = 0; dir < 2; ++dir) {
+            pa.Ucat[dir] = params + o.enc[dir].Ucat;
+            pa.r[dir] = w.enc_r[dir]; pa.u[dir] = w.enc_u[dir]; pa.c[dir] = w.enc_c[dir]; pa.p[dir] = w.enc_p[dir];
+            pa.dG[dir] = w.dGe[dir]; pa.dGx[dir] = w.dGex[dir];
+        }
+        pa.dcc = w.dcc; pa.mean_grad = w.dmean; pa.coef = w.xinv; pa.mask = x_mask; pa.cc = w.cc;
+        pa.bar = reinterpret_cast<unsigned*>(w.step_counters);
+        pa.Tx = Tx; pa.n = B; pa.D = D;
+        NATS_TRY(enc_persistent_bwd(ctx, st, pa));
+    }
+    if (fused && !persistent) NATS_CUDA_OK(memset_async(st, w.step_counters, 0, (size_t)w.step_counter_ints * sizeof(int)));
+    for (int s = Tx - 1; s >= 0 && !persistent; --s) {
         const int pf = s, pb = Tx - 1 - s;
         GateBwd g[2];
         memset(g, 0, sizeof(g));

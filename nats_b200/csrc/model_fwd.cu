@@ -27,6 +27,26 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
     const int S = gemm_pick_split(ctx, n, D3, D, 2);
     const int cfg = gemm_step_cfg(n);
     const long long strideP = 2LL * n * D3;
+    if (enc_persistent_eligible(ctx, n, D) && e.step_counters != nullptr) {
+        // the whole recurrence of both directions in ONE persistent weight-stationary launch (enc_persistent.cu)
+        EncPersistFwdArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        for (int dir = 0; dir < 2; ++dir) {
+            pa.Ucat[dir] = params + o.enc[dir].Ucat; pa.xproj[dir] = e.xproj[dir];
+            pa.r[dir] = e.r[dir]; pa.u[dir] = e.u[dir]; pa.c[dir] = e.c[dir]; pa.p[dir] = e.p[dir];
+        }
+        pa.mask = x_mask; pa.cc = e.cc; pa.ctxsum = e.ctxsum;
+        pa.bar = reinterpret_cast<unsigned*>(e.step_counters);
+        pa.Tx = Tx; pa.n = n; pa.D = D;
+        NATS_TRY(enc_persistent_fwd(ctx, st, pa));
+        NATS_TRY(mask_lengths(st, x_mask, Tx, n, e.xlen, e.xinv));
+        NATS_TRY(scale_rows(st, e.ctxsum, e.xinv, n, C, e.ctx_mean));
+        GemmProblem pi0 = gemm_problem(e.ctx_mean, C, params + o.ff_state_W, D, e.init_state, D, n, D, C);
+        pi0.bias = params + o.ff_state_b;
+        NATS_TRY(gemm_auto(ctx, st, pi0, false, false, e.gemm_scratch, e.gemm_scratch_floats));
+        NATS_TRY(tanh_inplace(st, e.init_state, (long long)n * D));
+        return 0;
+    }
     const bool fused = gru_step_eligible(n, D) && e.step_slab != nullptr;
     if (fused) NATS_CUDA_OK(memset_async(st, e.step_counters, 0, (size_t)e.step_counter_ints * sizeof(int)));
     for (int s = 0; s < Tx; ++s) {

@@ -77,6 +77,23 @@ int gru_step_fwd(const nats_ctx* ctx, cudaStream_t st, const GruStepFwd* dirs, i
 int gru_step_bwd(const nats_ctx* ctx, cudaStream_t st, const GruStepBwd* dirs, int ndir, int B, int D, float* slab,
                  int* counters);
 
+// ------------------------------------------------------------------ persistent encoder recurrence (enc_persistent.cu)
+struct EncPersistFwdArgs {
+    const float* Ucat[2]; const float* xproj[2]; const float* mask; float* cc;
+    float* r[2]; float* u[2]; float* c[2]; float* p[2];      // NULL = do not save
+    float* ctxsum; unsigned* bar; int Tx, n, D;
+};
+struct EncPersistBwdArgs {
+    const float* Ucat[2]; const float* dcc; const float* mean_grad; const float* coef; const float* mask; const float* cc;
+    const float* r[2]; const float* u[2]; const float* c[2]; const float* p[2];
+    float* dG[2]; float* dGx[2]; unsigned* bar; int Tx, n, D;
+};
+bool enc_persistent_eligible(const nats_ctx* ctx, int n, int D);
+void enc_persistent_enable(int on);
+int enc_persistent_setup(const nats_ctx* ctx);
+int enc_persistent_fwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistFwdArgs& a);
+int enc_persistent_bwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistBwdArgs& a);
+
 // ------------------------------------------------------------------ small elementwise / reductions
 int tanh_inplace(cudaStream_t st, float* x, long long n);
 // dst[i] = g[i] * (1 - y[i]^2)
@@ -134,6 +151,8 @@ struct AttBwd {
     float* dps;                                   // [B,A] output
     float* dpctx;                                 // [Tx,B,A] accumulated over steps
     float* gatt_part;                             // [B, 2A+1] accumulated over steps
+    float* dot_part;                              // scratch [B, ceil(Tx/16)]
+    float* soft_part;                             // scratch [B, ceil(Tx/16), 3A+1]
     int Tx, B, A, C;
 };
 int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a);

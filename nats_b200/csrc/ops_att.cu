@@ -15,7 +15,8 @@ namespace nats {
 namespace {
 
 constexpr int kAttThreads = 256;
-constexpr int kRowsPerCta = 32;   // scores / dalpha kernels: rows of Tx per CTA
+constexpr int kRowsPerCta = 32;   // scores kernel: rows of Tx per CTA
+constexpr int kBwdRows = 16;      // backward kernels: rows of Tx per CTA (more CTAs in flight for the cc re-stream)
 constexpr int kStages = 4;        // context kernel: bulk-copy ring depth
 constexpr int kStageRows = 16;    // rows of cc per stage
 constexpr int kMaxSlice = 256;    // columns per CTA (one per thread)
@@ -220,6 +221,7 @@ __global__ void att_bwd_ctx_kernel(const __grid_constant__ AttBwd a) {
 
 __global__ void __launch_bounds__(kAttThreads) att_bwd_dalpha_kernel(const __grid_constant__ AttBwd a) {
     extern __shared__ __align__(16) float s_dcraw[];
+    __shared__ float s_dot[kAttThreads / 32];
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.y;
@@ -228,14 +230,15 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_dalpha_kernel(const __gri
     const float m = a.ymask ? a.ymask[b] : 1.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec = ((a.C & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.cc) & 15) == 0);
-    const int t_end = min(a.Tx, (int)(blockIdx.x + 1) * kRowsPerCta);
-    for (int t = blockIdx.x * kRowsPerCta + warp; t < t_end; t += kAttThreads / 32) {
+    const int t_end = min(a.Tx, (int)(blockIdx.x + 1) * kBwdRows);
+    float dot = 0.f;                                   // this warp's share of sum_t alpha[t] * dalpha[t]
+    for (int t = blockIdx.x * kBwdRows + warp; t < t_end; t += kAttThreads / 32) {
         const float* row = a.cc + ((long long)t * a.B + b) * a.C;
         float s = 0.f;
         if (vec) {
             const int n4 = a.C >> 2;
             const float4* d4 = reinterpret_cast<const float4*>(s_dcraw);
-#pragma unroll 4
+#pragma unroll 8
             for (int i = lane; i < n4; i += 32) {
                 const float4 v = ldg_stream4(row + 4 * i);
                 const float4 d = d4[i];
@@ -247,56 +250,61 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_dalpha_kernel(const __gri
         s = warp_sum(s);
         if (lane == 0) {
             const long long o = (long long)b * a.Tx + t;
-            a.dalpha[o] = s + m * a.dacc_alpha[o];
+            const float da = s + m * a.dacc_alpha[o];
+            a.dalpha[o] = da;
+            dot = fmaf(a.alpha[o], da, dot);
         }
+    }
+    if (lane == 0) s_dot[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float d = 0.f;
+#pragma unroll
+        for (int w = 0; w < kAttThreads / 32; ++w) d += s_dot[w];
+        a.dot_part[(long long)b * gridDim.x + blockIdx.x] = d;       // fixed-order partial of the softmax-backward dot
     }
 }
 
-constexpr int kSoftThreads = 512;
+constexpr int kSoftThreads = 256;
 constexpr int kSoftWarps = kSoftThreads / 32;
 constexpr int kMaxAk = 8;   // A <= 256
 
+// grid (chunks of kBwdRows source positions, B).  Output partials part[b][chunk][3A+1] = {d ps, d U_att, d D_wei, d c_att}
 __global__ void __launch_bounds__(kSoftThreads) att_bwd_softmax_kernel(const __grid_constant__ AttBwd a) {
     extern __shared__ float sm[];
+    __shared__ float s_dot;
     pdl_trigger();
     pdl_wait();
-    __shared__ float red[32];
-    const int A = a.A, Tx = a.Tx, b = blockIdx.x, tid = threadIdx.x;
-    float* s_de = sm;                 // [Tx]
-    float* s_acc = s_de + Tx;         // [Tx]
-    float* s_ps = s_acc + Tx;         // [A]
+    const int A = a.A, Tx = a.Tx, b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x, tid = threadIdx.x;
+    float* s_ps = sm;                 // [A]
     float* s_dw = s_ps + A;           // [A]
     float* s_ua = s_dw + A;           // [A]
     float* s_part = s_ua + A;         // [warps][3][A]
-
-    float ldot = 0.f;
-    for (int t = tid; t < Tx; t += kSoftThreads) {
-        const long long o = (long long)b * Tx + t;
-        ldot += a.alpha[o] * a.dalpha[o];
-    }
-    const float dot = block_sum(ldot, red);
-    float lgc = 0.f;
-    for (int t = tid; t < Tx; t += kSoftThreads) {
-        const long long o = (long long)b * Tx + t;
-        const float de = a.alpha[o] * (a.dalpha[o] - dot);      // masked-softmax backward (nats.py:537-540)
-        s_de[t] = de;
-        s_acc[t] = a.acc_alpha[o];
-        lgc += de;
+    float* s_gc = s_part + kSoftWarps * 3 * A;   // [warps]
+    if (tid < 32) {                   // dot = sum_t alpha dalpha, from the fixed-order partials of the dalpha kernel
+        float d = 0.f;
+        for (int i = tid; i < nchunks; i += 32) d += a.dot_part[(long long)b * nchunks + i];
+        d = warp_sum(d);
+        if (tid == 0) s_dot = d;
     }
     for (int i = tid; i < A; i += kSoftThreads) {
         s_ps[i] = a.ps[(long long)b * A + i];
         s_dw[i] = __ldg(a.D_wei + i);
         s_ua[i] = __ldg(a.U_att + i);
     }
-    const float gc = block_sum(lgc, red);
     __syncthreads();
-
+    const float dot = s_dot;
     const int warp = tid >> 5, lane = tid & 31;
     float r_dps[kMaxAk], r_gu[kMaxAk], r_gd[kMaxAk];
 #pragma unroll
     for (int k = 0; k < kMaxAk; ++k) { r_dps[k] = 0.f; r_gu[k] = 0.f; r_gd[k] = 0.f; }
-    for (int t = warp; t < Tx; t += kSoftWarps) {
-        const float de = s_de[t], accv = s_acc[t];
+    float gc = 0.f;
+    const int t_end = min(Tx, (chunk + 1) * kBwdRows);
+    for (int t = chunk * kBwdRows + warp; t < t_end; t += kSoftWarps) {
+        const long long o = (long long)b * Tx + t;
+        const float de = a.alpha[o] * (a.dalpha[o] - dot);          // masked-softmax backward (nats.py:537-540)
+        const float accv = a.acc_alpha[o];
+        gc += de;
         const long long base = ((long long)t * a.B + b) * A;
         float rowsum = 0.f;
 #pragma unroll
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(kSoftThreads) att_bwd_softmax_kernel(const __g
             }
         }
         rowsum = warp_sum(rowsum);
-        if (lane == 0) a.dacc_alpha[(long long)b * Tx + t] += rowsum;           // through nats.py:532
+        if (lane == 0) a.dacc_alpha[o] += rowsum;                    // through nats.py:532
     }
 #pragma unroll
     for (int k = 0; k < kMaxAk; ++k) {
@@ -324,19 +332,33 @@ __global__ void __launch_bounds__(kSoftThreads) att_bwd_softmax_kernel(const __g
             s_part[(warp * 3 + 2) * A + i] = r_gd[k];
         }
     }
+    if (lane == 0) s_gc[warp] = gc;       // every lane of the warp holds the same gc (de is warp-uniform per row)
     __syncthreads();
-    for (int i = tid; i < A; i += kSoftThreads) {
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-        for (int w = 0; w < kSoftWarps; ++w) {
-            d0 += s_part[(w * 3 + 0) * A + i];
-            d1 += s_part[(w * 3 + 1) * A + i];
-            d2 += s_part[(w * 3 + 2) * A + i];
-        }
-        a.dps[(long long)b * A + i] = d0;
-        a.gatt_part[(long long)b * (2 * A + 1) + i] += d1;
-        a.gatt_part[(long long)b * (2 * A + 1) + A + i] += d2;
+    float* out = a.soft_part + ((long long)b * nchunks + chunk) * (3 * A + 1);
+    for (int i = tid; i < 3 * A; i += kSoftThreads) {
+        const int q = i / A, ia = i - q * A;
+        float d = 0.f;
+        for (int w = 0; w < kSoftWarps; ++w) d += s_part[(w * 3 + q) * A + ia];
+        out[i] = d;
     }
-    if (tid == 0) a.gatt_part[(long long)b * (2 * A + 1) + 2 * A] += gc;
+    if (tid == 0) {
+        float d = 0.f;
+        for (int w = 0; w < kSoftWarps; ++w) d += s_gc[w];
+        out[3 * A] = d;
+    }
+}
+
+// dps[b,:] = sum_chunks part ; gatt_part[b,:] += sum_chunks part   (fixed order)
+__global__ void att_bwd_reduce_kernel(const __grid_constant__ AttBwd a, int nchunks) {
+    pdl_trigger();
+    pdl_wait();
+    const int A = a.A, b = blockIdx.x;
+    for (int i = threadIdx.x; i < 3 * A + 1; i += blockDim.x) {
+        float d = 0.f;
+        for (int c = 0; c < nchunks; ++c) d += a.soft_part[((long long)b * nchunks + c) * (3 * A + 1) + i];
+        if (i < A) a.dps[(long long)b * A + i] = d;
+        else a.gatt_part[(long long)b * (2 * A + 1) + (i - A)] += d;     // [dU_att | dD_wei | dc_att]
+    }
 }
 
 inline size_t context_smem(int Tx, bool bulk, int slice_pad) {
@@ -406,16 +428,19 @@ int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a) {
         ProfScope ps(st, K_ATT_BWD_CTX);
         NATS_CUDA_OK(launch_pdl(att_bwd_ctx_kernel, dim3(cdiv(a.B * a.C, 256)), dim3(256), 0, st, a));
     }
+    const int nchunks = cdiv(a.Tx, kBwdRows);
+    NATS_REQUIRE(a.dot_part != nullptr && a.soft_part != nullptr, "attention backward scratch");
     {
-        dim3 grid(cdiv(a.Tx, kRowsPerCta), a.B);
+        dim3 grid(nchunks, a.B);
         ProfScope ps(st, K_ATT_BWD_DALPHA, 2.0 * a.Tx * a.B * a.C, 4.0 * ((double)a.Tx * a.B * a.C + 2.0 * a.B * a.Tx));
         NATS_CUDA_OK(launch_pdl(att_bwd_dalpha_kernel, grid, dim3(kAttThreads), (size_t)a.C * sizeof(float), st, a));
     }
     {
-        const size_t smem = ((size_t)2 * a.Tx + 3 * a.A + (size_t)kSoftWarps * 3 * a.A) * sizeof(float);
-        NATS_REQUIRE(smem <= (size_t)g_att_dyn_limit, "source too long for the attention backward kernel");
+        const size_t smem = ((size_t)3 * a.A + (size_t)kSoftWarps * 3 * a.A + kSoftWarps) * sizeof(float);
+        dim3 grid(nchunks, a.B);
         ProfScope ps(st, K_ATT_BWD_SOFTMAX, 0.0, 12.0 * a.Tx * a.B * a.A);
-        NATS_CUDA_OK(launch_pdl(att_bwd_softmax_kernel, dim3(a.B), dim3(kSoftThreads), smem, st, a));
+        NATS_CUDA_OK(launch_pdl(att_bwd_softmax_kernel, grid, dim3(kSoftThreads), smem, st, a));
+        NATS_CUDA_OK(launch_pdl(att_bwd_reduce_kernel, dim3(a.B), dim3(128), 0, st, a, nchunks));
     }
     return 0;
 }

@@ -134,6 +134,8 @@ struct TrainWS {
     float* dh_elem;      // [2, B, D]   elementwise part of d h_{t-1} (per direction for the encoder)
     float* dh1_elem;     // [B, D]
     float* gatt_part;    // [B, 2A+1]   per-sample partial sums of d U_att | d D_wei | d c_att over all steps
+    float* att_dot_part; // [B, ceil(Tx/16)]           attention-backward scratch
+    float* att_soft_part;// [B, ceil(Tx/16), 3A+1]
     float* dcc;          // [Tx*B, C]
     float* dinit;        // [B, D]
     float* dmean;        // [B, C]
@@ -181,6 +183,8 @@ inline TrainWS carve_train(const nats_dims_t& d, int Tx, int Ty, int B, void* ba
     w.dalpha = c.f((int64_t)B * Tx); w.dacc_alpha = c.f((int64_t)B * Tx); w.dacc_ctx = c.f(2 * B * C);
     w.dh_elem = c.f(2 * B * D); w.dh1_elem = c.f(B * D);
     w.gatt_part = c.f(B * (2 * A + 1));
+    w.att_dot_part = c.f((int64_t)B * ((Tx + 15) / 16));
+    w.att_soft_part = c.f((int64_t)B * ((Tx + 15) / 16) * (3 * A + 1));
     w.dcc = c.f(XB * C); w.dinit = c.f(B * D); w.dmean = c.f(B * C);
     for (int i = 0; i < 2; ++i) { w.dGe[i] = c.f(XB * 3 * D); w.dGex[i] = c.f(XB * 3 * D); }
     w.demb_x = c.f(XB * W);
