@@ -5,12 +5,16 @@
 // product + gate kernel), most of it fixed overhead and re-streaming the 12 MB weight matrix from L2.  Here every CTA
 // owns `upc` hidden units of one direction for the whole sequence:
 //   * its 3*upc columns of [U|Ux] (forward) / its upc rows of [U|Ux] (backward) are loaded ONCE into shared memory
-//     (168 KB at D = 1000, upc = 14: 72 CTAs per direction, 144 of the 148 SMs);
-//   * per step it streams the previous state h_{t-1} (forward) / the gate derivatives dG_{t+1} (backward) from L2 in
-//     128-deep chunks (register-staged, transposed + XOR-swizzled into shared memory, next chunk in flight during compute),
-//     accumulates an 8(batch) x 4(column) register tile per thread with exact fp32 FMAs, K split over 8 thread groups;
-//   * since a CTA sees the FULL K extent of its units, the GRU gate arithmetic (and its reverse) is finished in place --
-//     no split-K slabs, no second kernel -- and h_t / dG_t are published for the other CTAs;
+//     (192 KB at D = 1000: 72 + 72 CTAs forward, 63 + 63 backward, one per SM);
+//   * the K extent is cut into 8-deep slices dealt round-robin to the 16 warps.  A warp stages ITS slice of h_{t-1}
+//     (forward) / dG_{t+1} (backward) from L2 into a private 1 KB shared buffer (two 16-byte loads per lane, the next
+//     slice in flight during the arithmetic, only __syncwarp in the loop) and accumulates a 32 x ncol partial product
+//     with packed fp32 FMAs (FFMA2, exact fp32): lanes = 4 batch groups x 8 column groups, 8x6 register tile (forward)
+//     or 2 slices x 4 x 4, 8x4 tile (backward); every shared load is conflict-free or a broadcast, addresses are
+//     immediates of two base registers;
+//   * the 16 partials are added in a FIXED order through shared-memory slabs (deterministic), and since the CTA sees
+//     the full K extent of its units the GRU gate arithmetic (and its reverse) is finished in place -- no split-K slabs
+//     in global memory, no second kernel -- and h_t / dG_t are published for the other CTAs;
 //   * one arrive/spin barrier per direction and step (monotonic counter in L2) orders the steps.
 // The grid must be co-resident (2*P CTAs <= #SMs, one CTA per SM by shared-memory footprint); a spinning CTA traps
 // after ~2 s instead of hanging the GPU.
@@ -20,10 +24,13 @@ namespace nats {
 
 namespace {
 
-constexpr int kKC = 128;        // chunk depth
-constexpr int kTB = 8;          // register tile: batch rows
-constexpr int kTC = 8;          // register tile: columns  (8x8: 4 LDS.128 per 64 FMA -- the shared-memory port keeps up)
-constexpr int kMaxThreads = 384;
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kChunk = 8 * kWarps;      // k rows consumed per round of all warps (8 per warp)
+constexpr int kBP = 32;                 // batch rows of the CTA tile (n <= 32)
+constexpr int kHS = 36;                 // row stride of a staging buffer: 32 batch columns + 4 (the two slices of a warp hit disjoint banks)
+constexpr int kStageWarp = 8 * kHS;     // floats per warp-private staging buffer
+constexpr int kStageFloats = kWarps * kStageWarp;
 
 struct EncPFwd {
     const float* Ucat[2];       // [D,3D]
@@ -34,7 +41,7 @@ struct EncPFwd {
     float* ctxsum;              // [n,2D]
     unsigned* bar;              // [2] zero-initialised
     long long* dbg;             // optional [8] phase cycle counters of CTA (0,0)
-    int Tx, n, D, upc, P, BP, NS;   // BP = batch padded to a power of two >= 8; NS = slabs of the K-split reduction
+    int Tx, n, D, upc, P, NS;   // NS = slabs of the cross-warp reduction
 };
 
 struct EncPBwd {
@@ -47,17 +54,13 @@ struct EncPBwd {
     const float* r[2]; const float* u[2]; const float* c[2]; const float* p[2];
     float* dG[2]; float* dGx[2];   // [Tx*n,3D] by position
     unsigned* bar;
-    int Tx, n, D, upc, P, BP, NS;
+    long long* dbg;
+    int Tx, n, D, upc, P, NS;
 };
 
 __device__ __forceinline__ float4 ldcg4(const float* p) {
     float4 r;
     asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float ldcg1(const float* p) {
-    float r;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
 
@@ -72,7 +75,6 @@ __device__ __forceinline__ void dir_barrier(unsigned* ctr, unsigned target) {
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             if (v >= target) break;
-            __nanosleep(40);
             if (clock64() - t0 > 4000000000LL) __trap();        // ~2 s: never hang the device
         } while (true);
         __threadfence();
@@ -80,89 +82,162 @@ __device__ __forceinline__ void dir_barrier(unsigned* ctr, unsigned target) {
     __syncthreads();
 }
 
-// Stage one [rows x kKC] chunk of a row-major [rows, ld] global matrix into shared memory TRANSPOSED as hT[kk][row],
-// float4 columns XOR-swizzled with (kk >> 2) & 7 (conflict-free transposing stores, 16-byte aligned reads).
-template <int NV>
-__device__ __forceinline__ void chunk_load(const float* __restrict__ src, long long ld, int rows, int K, int k0, int BP,
-                                           int tid, int nthreads, float4 (&v)[NV]) {
-    const int per_row = kKC / 4;
+// Packed fp32 FMA (sm_100 FFMA2): two exact fp32 FMAs per lane and instruction.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+
+// 8 x TC register tile held as packed pairs: for row pair i and column pair j
+//   X[i][j] = (acc[2i][2j],   acc[2i+1][2j+1])   += (h[2i], h[2i+1]) * (w[2j],   w[2j+1])
+//   Y[i][j] = (acc[2i][2j+1], acc[2i+1][2j])     += (h[2i], h[2i+1]) * (w[2j+1], w[2j])
+// so the h pairs and the w pairs come straight out of the vector shared loads; the swapped w pair is an operand
+// modifier of FFMA2 (no instruction).
+template <int TC>
+struct Frag {
+    u64 X[4][TC / 2], Y[4][TC / 2];
+    __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int f = tid + i * nthreads;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f < BP * per_row) {
-            const int b = f / per_row, k4 = f - b * per_row;
-            const int k = k0 + 4 * k4;
-            if (b < rows && k < K) {
-                const float* p = src + (long long)b * ld + k;
-                if (k + 3 < K) val = ldcg4(p);
-                else {
-                    val.x = ldcg1(p);
-                    if (k + 1 < K) val.y = ldcg1(p + 1);
-                    if (k + 2 < K) val.z = ldcg1(p + 2);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TC / 2; ++j) { X[i][j] = 0ull; Y[i][j] = 0ull; }
+    }
+    __device__ __forceinline__ void get(float (&acc)[8][TC]) const {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TC / 2; ++j) {
+                unpack2(X[i][j], acc[2 * i][2 * j], acc[2 * i + 1][2 * j + 1]);
+                unpack2(Y[i][j], acc[2 * i][2 * j + 1], acc[2 * i + 1][2 * j]);
+            }
+    }
+};
+
+// Partial product of this warp's K slices:  f += src[0..nrows)[k] (x) Wt[k][cols of this lane]   over k in the warp's slices.
+//   src: row-major [nrows, ld] in global memory (written by other CTAs in the previous step: read through L2)
+//   Wt : shared, [K][NCOL], NCOL = (8/SL)*TC
+//   hb : this warp's private staging buffer [8][kHS]
+// lane layout: slice sl = lane / (32/SL) (takes rows SL*t + sl of the staged 8), then bg (4 groups of 8 batch rows)
+// x cg (8/SL groups of TC columns).
+template <int TC, int SL, int PF>
+__device__ __forceinline__ void kslice_product(const float* __restrict__ src, long long ld, int nrows, int K,
+                                               const float* __restrict__ Wt, float* __restrict__ hb, int warp, int lane,
+                                               int rot, Frag<TC>& f) {
+    constexpr int NCG = 8 / SL, NCOL = NCG * TC, KT = 8 / SL, LPS = 32 / SL;
+    const int sl = lane / LPS, l2 = lane % LPS, bg = l2 / NCG, cg = l2 % NCG;
+    const float* hrd = hb + sl * kHS + bg * 8;
+    const float* wrd = Wt + (size_t)(8 * warp + sl) * NCOL + cg * TC;
+    const float* grow = src + (long long)lane * ld + 8 * warp;      // lane = batch row of the staged slice
+    const bool rowok = lane < nrows;
+    const int nch = (K + kChunk - 1) / kChunk;
+    // PF slices in flight per warp (registers): the L2 round trip under load is > 1000 cycles
+    float4 v[PF][2];
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        v[p][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[p][1] = v[p][0];
+        const int cc = (p + rot) % nch;      // CTAs walk the K extent from different starting chunks: no L2 hot spot
+        if (rowok && p < nch && cc * kChunk + 8 * warp < K) { v[p][0] = ldcg4(grow + cc * kChunk); v[p][1] = ldcg4(grow + cc * kChunk + 4); }
+    }
+    for (int c0 = 0; c0 < nch; c0 += PF) {
+#pragma unroll
+        for (int p = 0; p < PF; ++p) {
+            const int c = c0 + p;
+            if (c >= nch) break;
+            const int cc = (c + rot) % nch;
+            const bool act = cc * kChunk + 8 * warp < K;            // warp-uniform (K % 8 == 0)
+            __syncwarp();
+            hb[0 * kHS + lane] = v[p][0].x; hb[1 * kHS + lane] = v[p][0].y; hb[2 * kHS + lane] = v[p][0].z; hb[3 * kHS + lane] = v[p][0].w;
+            hb[4 * kHS + lane] = v[p][1].x; hb[5 * kHS + lane] = v[p][1].y; hb[6 * kHS + lane] = v[p][1].z; hb[7 * kHS + lane] = v[p][1].w;
+            __syncwarp();
+            const int cn = (c + PF + rot) % nch;
+            if (rowok && c + PF < nch && cn * kChunk + 8 * warp < K) {
+                v[p][0] = ldcg4(grow + cn * kChunk);
+                v[p][1] = ldcg4(grow + cn * kChunk + 4);
+            }
+            if (act) {
+                const float* w = wrd + (size_t)cc * kChunk * NCOL;
+#pragma unroll
+                for (int t = 0; t < KT; ++t) {
+                    const float4 h0 = *reinterpret_cast<const float4*>(hrd + SL * t * kHS);
+                    const float4 h1 = *reinterpret_cast<const float4*>(hrd + SL * t * kHS + 4);
+                    const u64 hp[4] = {pack2(h0.x, h0.y), pack2(h0.z, h0.w), pack2(h1.x, h1.y), pack2(h1.z, h1.w)};
+                    float wv[TC];
+                    if (TC == 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(w + SL * t * NCOL);
+                        wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TC / 2; ++j) {
+                            const float2 q = *reinterpret_cast<const float2*>(w + SL * t * NCOL + 2 * j);
+                            wv[2 * j] = q.x; wv[2 * j + 1] = q.y;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < TC / 2; ++j) {
+                        const u64 wp = pack2(wv[2 * j], wv[2 * j + 1]);
+                        const u64 ws = pack2(wv[2 * j + 1], wv[2 * j]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            ffma2(f.X[i][j], hp[i], wp);
+                            ffma2(f.Y[i][j], hp[i], ws);
+                        }
+                    }
                 }
             }
         }
-        v[i] = val;
-    }
-}
-template <int NV>
-__device__ __forceinline__ void chunk_store(float* __restrict__ hT, int BP, int tid, int nthreads, const float4 (&v)[NV]) {
-    const int per_row = kKC / 4;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int f = tid + i * nthreads;
-        if (f < BP * per_row) {
-            const int b = f / per_row, k4 = f - b * per_row;
-            const int col = 4 * (((b >> 2) ^ (k4 & ((BP >> 2) - 1) & 7))) + (b & 3);
-            hT[(4 * k4 + 0) * BP + col] = v[i].x;
-            hT[(4 * k4 + 1) * BP + col] = v[i].y;
-            hT[(4 * k4 + 2) * BP + col] = v[i].z;
-            hT[(4 * k4 + 3) * BP + col] = v[i].w;
-        }
     }
 }
 
-// acc[8][8] += hT[kk][bg*8 .. +7] (x) W[k][cg*8 .. +7]   for this thread's k-slice (kk = ks, ks+KS, ...) of the chunk
-__device__ __forceinline__ void chunk_fma(const float* __restrict__ hT, const float* __restrict__ Wt, int ncolp, int BP,
-                                          int k0, int K, int ks, int KS, int bg, int cg, float (&acc)[kTB][kTC]) {
-    const int kmax = min(kKC, K - k0);
-    const int swm = ((BP >> 2) - 1) & 7;
-#pragma unroll 2
-    for (int kk = ks; kk < kmax; kk += KS) {
-        const int sw = (kk >> 2) & swm;
-        const float4 h0 = *reinterpret_cast<const float4*>(hT + kk * BP + 4 * ((2 * bg) ^ sw));
-        const float4 h1 = *reinterpret_cast<const float4*>(hT + kk * BP + 4 * ((2 * bg + 1) ^ sw));
-        const float* wr = Wt + (size_t)(k0 + kk) * ncolp + 8 * cg;
-        const float4 w0 = *reinterpret_cast<const float4*>(wr);
-        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-        const float hv[kTB] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        const float wv[kTC] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int i = 0; i < kTB; ++i)
-#pragma unroll
-            for (int j = 0; j < kTC; ++j) acc[i][j] = fmaf(hv[i], wv[j], acc[i][j]);
-    }
+// Slabs are kept in FRAGMENT order: element (row b, column col) of the 32 x NCOL tile lives at
+//   ((i * LPS + bg*NCG + cg) * TC + j),  b = 8*bg + i,  col = cg*TC + j          (conflict-free vector stores)
+template <int TC, int SL>
+__device__ __forceinline__ int slab_index(int b, int col) {
+    constexpr int NCG = 8 / SL, LPS = 32 / SL;
+    const int bg = b >> 3, i = b & 7, cg = col / TC, j = col - cg * TC;
+    return (i * LPS + bg * NCG + cg) * TC + j;
 }
 
-// K-split reduction: group ks adds its tile into slab (ks % kNS) in round (ks / kNS); rounds are separated by barriers.
-__device__ __forceinline__ void reduce_to_slabs(float* __restrict__ slabs, int BP, int ncolp, int ks, int KS, int NS, int bg,
-                                                int cg, bool worker, const float (&acc)[kTB][kTC]) {
-    const int rounds = (KS + NS - 1) / NS;
+// Cross-warp reduction in a fixed order: warp w adds its partial into slab (w % NS) in round (w / NS).
+template <int TC, int SL>
+__device__ __forceinline__ void reduce_to_slabs(float* __restrict__ slabs, int NS, int warp, int lane, const Frag<TC>& f) {
+    constexpr int LPS = 32 / SL, SLAB = 8 * LPS * TC;
+    float acc[8][TC];
+    f.get(acc);
+    if (SL == 2) {          // the two slices of a warp hold the same tile positions in lanes l and l + 16
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < TC; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
+    }
+    const int rounds = (kWarps + NS - 1) / NS;
     for (int r = 0; r < rounds; ++r) {
-        if (worker && ks / NS == r) {
-            float* sl = slabs + (size_t)(ks % NS) * BP * ncolp;
+        if (warp / NS == r && lane < LPS) {
+            float* sl = slabs + (size_t)(warp % NS) * SLAB;
 #pragma unroll
-            for (int i = 0; i < kTB; ++i) {
-                float4* p0 = reinterpret_cast<float4*>(sl + (size_t)(bg * kTB + i) * ncolp + cg * kTC);
-                float4 a0 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                float4 a1 = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-                if (r > 0) {
-                    const float4 o0 = p0[0], o1 = p0[1];
-                    a0.x += o0.x; a0.y += o0.y; a0.z += o0.z; a0.w += o0.w;
-                    a1.x += o1.x; a1.y += o1.y; a1.z += o1.z; a1.w += o1.w;
+            for (int i = 0; i < 8; ++i) {
+                float* p = sl + (i * LPS + lane) * TC;
+                if (TC == 4) {
+                    float4 a = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                    if (r > 0) {
+                        const float4 o = *reinterpret_cast<const float4*>(p);
+                        a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                    }
+                    *reinterpret_cast<float4*>(p) = a;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TC / 2; ++j) {
+                        float2 a = make_float2(acc[i][2 * j], acc[i][2 * j + 1]);
+                        if (r > 0) {
+                            const float2 o = *reinterpret_cast<const float2*>(p + 2 * j);
+                            a.x += o.x; a.y += o.y;
+                        }
+                        *reinterpret_cast<float2*>(p + 2 * j) = a;
+                    }
                 }
-                p0[0] = a0; p0[1] = a1;
             }
         }
         __syncthreads();
@@ -170,292 +245,221 @@ __device__ __forceinline__ void reduce_to_slabs(float* __restrict__ slabs, int B
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int NV>
-__global__ void __launch_bounds__(kMaxThreads, 1) enc_persist_fwd_kernel(const __grid_constant__ EncPFwd a) {
+constexpr int kFwdTC = 6, kFwdSL = 1, kFwdCols = (8 / kFwdSL) * kFwdTC;        // 48 columns = 3 gates x <= 16 units
+constexpr int kFwdSlab = 8 * (32 / kFwdSL) * kFwdTC;
+constexpr int kFwdPF = 2;
+
+__global__ void __launch_bounds__(kThreads, 1) enc_persist_fwd_kernel(const __grid_constant__ EncPFwd a) {
     extern __shared__ __align__(16) float sm[];
     const int dir = blockIdx.y, D = a.D, n = a.n, C = 2 * D, D3 = 3 * D, upc = a.upc;
     const int j0 = blockIdx.x * upc;
     const int nu = min(upc, D - j0);
-    const int ncol = 3 * upc, ncolp = (ncol + 7) & ~7;
-    const int BP = a.BP;
-    const int NBG = BP / kTB, NCG = ncolp / kTC;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int KS = nthreads / (NBG * NCG);
-    float* Wt = sm;                                   // [D][ncolp]   column = gate*upc + unit
-    float* buf = Wt + (size_t)D * ncolp;              // chunk ring [2][kKC][BP]  /  reduction slabs [NS][BP][ncolp]
-    const int ring = kKC * BP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* Wt = sm;                                   // [D][48]   column = gate*upc + unit
+    float* buf = Wt + (size_t)D * kFwdCols;           // staging buffers [16][8][kHS]  /  reduction slabs [NS][fragment order]
 
     {   // weights of this CTA's units, once
         const float* U = a.Ucat[dir];
-        for (int idx = tid; idx < D * ncolp; idx += nthreads) {
-            const int k = idx / ncolp, col = idx - k * ncolp;
+        for (int idx = tid; idx < D * kFwdCols; idx += kThreads) {
+            const int k = idx / kFwdCols, col = idx - k * kFwdCols;
             const int g = col / upc, uu = col - g * upc;
-            Wt[idx] = (col < ncol && uu < nu) ? __ldg(U + (long long)k * D3 + g * D + j0 + uu) : 0.f;
+            Wt[idx] = (g < 3 && uu < nu) ? __ldg(U + (long long)k * D3 + g * D + j0 + uu) : 0.f;
         }
     }
-    const int cg = tid % NCG, bg = (tid / NCG) % NBG, ks = tid / (NCG * NBG);
-    const bool worker = ks < KS;
-    // this thread's (batch, unit) pairs in the gate phase: the same ones at every step -> carries live in registers
-    constexpr int kPairs = 2;
-    float h_carry[kPairs], cs_carry[kPairs];
-#pragma unroll
-    for (int q = 0; q < kPairs; ++q) { h_carry[q] = 0.f; cs_carry[q] = 0.f; }
+    // this thread's (batch, unit) pair in the gate phase: the same one at every step -> carries live in registers
+    const bool gate_thread = tid < n * nu;
+    const int gb = gate_thread ? tid / nu : 0, guu = gate_thread ? tid - gb * nu : 0;
+    const int gj = j0 + guu;
+    float h_carry = 0.f, cs_carry = 0.f;
+    const int nsl = min(kWarps, a.NS);
     __syncthreads();
 
-    long long t_comp = 0, t_gate = 0, t_bar = 0, t_first = 0;
+    long long t_comp = 0, t_red = 0, t_gate = 0, t_bar = 0;
     for (int s = 0; s < a.Tx; ++s) {
         const int pos = dir == 0 ? s : a.Tx - 1 - s;
         const int prev = dir == 0 ? pos - 1 : pos + 1;
         const long long c0 = clock64();
-        long long c1 = c0;
         // gate inputs of this step (independent of h_{t-1}): requested now, consumed after the product
-        float gx[kPairs][3], gm[kPairs];
-#pragma unroll
-        for (int q = 0; q < kPairs; ++q) {
-            const int idx = tid + q * nthreads;
-            gx[q][0] = gx[q][1] = gx[q][2] = 0.f; gm[q] = 1.f;
-            if (idx < n * nu) {
-                const int b = idx / nu, uu = idx - b * nu;
-                const float* x = a.xproj[dir] + ((long long)pos * n + b) * D3 + j0 + uu;
-                gx[q][0] = __ldg(x); gx[q][1] = __ldg(x + D); gx[q][2] = __ldg(x + 2 * D);
-                if (a.mask) gm[q] = __ldg(a.mask + (long long)pos * n + b);
-            }
+        float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f, gm = 1.f;
+        if (gate_thread) {
+            const float* x = a.xproj[dir] + ((long long)pos * n + gb) * D3 + gj;
+            gx0 = __ldg(x); gx1 = __ldg(x + D); gx2 = __ldg(x + 2 * D);
+            if (a.mask) gm = __ldg(a.mask + (long long)pos * n + gb);
         }
-        float acc[kTB][kTC];
-#pragma unroll
-        for (int i = 0; i < kTB; ++i)
-#pragma unroll
-            for (int j = 0; j < kTC; ++j) acc[i][j] = 0.f;
-
+        long long c1 = c0;
         if (s > 0) {
-            const float* hsrc = a.cc + (long long)prev * n * C + dir * D;     // rows b, stride C
-            const int nch = (D + kKC - 1) / kKC;
-            float4 regs[NV];
-            chunk_load<NV>(hsrc, C, n, D, 0, BP, tid, nthreads, regs);
-            chunk_store<NV>(buf, BP, tid, nthreads, regs);
-            __syncthreads();
+            Frag<kFwdTC> f;
+            f.clear();
+            kslice_product<kFwdTC, kFwdSL, kFwdPF>(a.cc + (long long)prev * n * C + dir * D, C, n, D, Wt, buf + warp * kStageWarp, warp, lane, (int)blockIdx.x, f);
+            __syncthreads();                          // every warp is done with its staging buffer: the slabs alias them
             c1 = clock64();
-            for (int ch = 0; ch < nch; ++ch) {
-                const float* cur = buf + (ch & 1) * ring;
-                if (ch + 1 < nch) chunk_load<NV>(hsrc, C, n, D, (ch + 1) * kKC, BP, tid, nthreads, regs);
-                if (worker) chunk_fma(cur, Wt, ncolp, BP, ch * kKC, D, ks, KS, bg, cg, acc);
-                if (ch + 1 < nch) chunk_store<NV>(buf + ((ch + 1) & 1) * ring, BP, tid, nthreads, regs);
-                __syncthreads();
-            }
-            reduce_to_slabs(buf, BP, ncolp, ks, KS, a.NS, bg, cg, worker, acc);
+            reduce_to_slabs<kFwdTC, kFwdSL>(buf, a.NS, warp, lane, f);
         }
         const long long c2 = clock64();
-        // gates for the (b, unit) pairs of this thread (nats.py:341-354)
-#pragma unroll
-        for (int q = 0; q < kPairs; ++q) {
-            const int idx = tid + q * nthreads;
-            if (idx < n * nu) {
-                const int b = idx / nu, uu = idx - b * nu;
-                const int j = j0 + uu;
-                float gr = gx[q][0], gu = gx[q][1], pp = 0.f;
-                if (s > 0) {
-                    const int nsl = KS < a.NS ? KS : a.NS;
-                    for (int sl = 0; sl < nsl; ++sl) {
-                        const float* pr = buf + ((size_t)sl * BP + b) * ncolp;
-                        gr += pr[uu]; gu += pr[upc + uu]; pp += pr[2 * upc + uu];
-                    }
+        // gates for the (b, unit) pair of this thread (nats.py:341-354)
+        if (gate_thread) {
+            float gr = gx0, gu = gx1, pp = 0.f;
+            if (s > 0) {
+                const int i0 = slab_index<kFwdTC, kFwdSL>(gb, guu), i1 = slab_index<kFwdTC, kFwdSL>(gb, upc + guu),
+                          i2 = slab_index<kFwdTC, kFwdSL>(gb, 2 * upc + guu);
+                for (int sl = 0; sl < nsl; ++sl) {
+                    const float* pr = buf + (size_t)sl * kFwdSlab;
+                    gr += pr[i0]; gu += pr[i1]; pp += pr[i2];
                 }
-                const float r = sigmoidf_(gr), uz = sigmoidf_(gu);
-                const float c = tanhf(pp * r + gx[q][2]);
-                const float hp = h_carry[q];
-                const float hn = uz * hp + (1.f - uz) * c;
-                const float m = gm[q];
-                const float h = m * hn + (1.f - m) * hp;
-                h_carry[q] = h;
-                cs_carry[q] += m * h;
-                a.cc[((long long)pos * n + b) * C + dir * D + j] = h;
-                if (a.r[dir]) {
-                    const long long o = ((long long)pos * n + b) * D + j;
-                    a.r[dir][o] = r; a.u[dir][o] = uz; a.c[dir][o] = c; a.p[dir][o] = pp;
-                }
+            }
+            const float r = sigmoidf_(gr), uz = sigmoidf_(gu);
+            const float c = tanhf(pp * r + gx2);
+            const float hp = h_carry;
+            const float hn = uz * hp + (1.f - uz) * c;
+            const float h = gm * hn + (1.f - gm) * hp;
+            h_carry = h;
+            cs_carry += gm * h;
+            a.cc[((long long)pos * n + gb) * C + dir * D + gj] = h;
+            if (a.r[dir]) {
+                const long long o = ((long long)pos * n + gb) * D + gj;
+                a.r[dir][o] = r; a.u[dir][o] = uz; a.c[dir][o] = c; a.p[dir][o] = pp;
             }
         }
         const long long c3 = clock64();
         if (s + 1 < a.Tx) dir_barrier(a.bar + dir, (unsigned)a.P * (unsigned)(s + 1));
         const long long c4 = clock64();
-        t_first += c1 - c0; t_comp += c2 - c1; t_gate += c3 - c2; t_bar += c4 - c3;
+        t_comp += c1 - c0; t_red += c2 - c1; t_gate += c3 - c2; t_bar += c4 - c3;
     }
-#pragma unroll
-    for (int q = 0; q < kPairs; ++q) {
-        const int idx = tid + q * nthreads;
-        if (idx < n * nu) {
-            const int b = idx / nu, uu = idx - b * nu;
-            a.ctxsum[(long long)b * C + dir * D + j0 + uu] += cs_carry[q];
-        }
-    }
+    if (gate_thread) a.ctxsum[(long long)gb * C + dir * D + gj] += cs_carry;
     if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-        a.dbg[0] = t_first; a.dbg[1] = t_comp; a.dbg[2] = t_gate; a.dbg[3] = t_bar;
+        a.dbg[0] = t_comp; a.dbg[1] = t_red; a.dbg[2] = t_gate; a.dbg[3] = t_bar;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// CTA owns units j0..j0+upc-1: out[b][u] = sum_k dG_{t+1}[b,k] * Ucat[j0+u, k]   (K = 3D), then the gate backward of
-// step t for its units; the elementwise carry of d h stays in shared memory across steps.
-template <int NV>
-__global__ void __launch_bounds__(kMaxThreads, 1) enc_persist_bwd_kernel(const __grid_constant__ EncPBwd a) {
+// CTA owns units j0..j0+upc-1 (upc <= 16): out[b][u] = sum_k dG_{t+1}[b,k] * Ucat[j0+u, k]   (K = 3D), then the gate
+// backward of step t for its units; the elementwise carry of d h stays in a register across steps.
+constexpr int kBwdTC = 4, kBwdSL = 2, kBwdCols = (8 / kBwdSL) * kBwdTC;        // 16 columns
+constexpr int kBwdSlab = 8 * (32 / kBwdSL) * kBwdTC;
+constexpr int kBwdPF = 4;
+
+__global__ void __launch_bounds__(kThreads, 1) enc_persist_bwd_kernel(const __grid_constant__ EncPBwd a) {
     extern __shared__ __align__(16) float sm[];
     const int dir = blockIdx.y, D = a.D, n = a.n, C = 2 * D, D3 = 3 * D, upc = a.upc;
     const int j0 = blockIdx.x * upc;
     const int nu = min(upc, D - j0);
-    const int ncolp = (upc + 7) & ~7;
-    const int BP = a.BP;
-    const int NBG = BP / kTB, NCG = ncolp / kTC;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int KS = nthreads / (NBG * NCG);
-    float* Wt = sm;                                   // [3D][ncolp]   Wt[k][u] = Ucat[j0+u, k]
-    float* buf = Wt + (size_t)D3 * ncolp;             // chunk ring [2][kKC][BP]  /  reduction slabs [NS][BP][ncolp]
-    const int ring = kKC * BP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* Wt = sm;                                   // [3D][16]   Wt[k][u] = Ucat[j0+u, k]
+    float* buf = Wt + (size_t)D3 * kBwdCols;
 
     {
         const float* U = a.Ucat[dir];
-        for (int idx = tid; idx < D3 * ncolp; idx += nthreads) {
+        for (int idx = tid; idx < D3 * kBwdCols; idx += kThreads) {
             const int uu = idx / D3, k = idx - uu * D3;      // coalesced along k
-            Wt[(size_t)k * ncolp + uu] = (uu < nu) ? __ldg(U + (long long)(j0 + uu) * D3 + k) : 0.f;
+            Wt[(size_t)k * kBwdCols + uu] = (uu < nu) ? __ldg(U + (long long)(j0 + uu) * D3 + k) : 0.f;
         }
     }
-    const int cg = tid % NCG, bg = (tid / NCG) % NBG, ks = tid / (NCG * NBG);
-    const bool worker = ks < KS;
-    constexpr int kPairs = 2;
-    float carry[kPairs];                              // elementwise part of d h_{t-1} of this thread's (b, unit) pairs
-#pragma unroll
-    for (int q = 0; q < kPairs; ++q) carry[q] = 0.f;
+    const bool gate_thread = tid < n * nu;
+    const int gb = gate_thread ? tid / nu : 0, guu = gate_thread ? tid - gb * nu : 0;
+    const int gj = j0 + guu;
+    const int gi = slab_index<kBwdTC, kBwdSL>(gb, guu);
+    const int nsl = min(kWarps, a.NS);
+    float carry = 0.f;                                // elementwise part of d h_{t-1}
+    const float mg = (gate_thread && a.mean_grad) ? __ldg(a.coef + gb) * __ldg(a.mean_grad + (long long)gb * C + dir * D + gj) : 0.f;
     __syncthreads();
 
+    long long t_comp = 0, t_red = 0, t_gate = 0, t_bar = 0;
     for (int s = a.Tx - 1; s >= 0; --s) {
         const int pos = dir == 0 ? s : a.Tx - 1 - s;
         const int prev = dir == 0 ? pos - 1 : pos + 1;            // position of h_{t-1}
         const int nextp = dir == 0 ? pos + 1 : pos - 1;           // position processed by step s+1
+        const long long c0 = clock64();
         // gate-backward inputs of this step: requested before the product, consumed after it
-        float g_dcc[kPairs], g_m[kPairs], g_r[kPairs], g_u[kPairs], g_c[kPairs], g_p[kPairs], g_hp[kPairs], g_mg[kPairs];
-#pragma unroll
-        for (int q = 0; q < kPairs; ++q) {
-            const int idx = tid + q * nthreads;
-            g_dcc[q] = g_r[q] = g_u[q] = g_c[q] = g_p[q] = g_hp[q] = g_mg[q] = 0.f; g_m[q] = 1.f;
-            if (idx < n * nu) {
-                const int b = idx / nu, uu = idx - b * nu;
-                const int j = j0 + uu;
-                const long long o = ((long long)pos * n + b) * D + j;
-                g_dcc[q] = __ldg(a.dcc + ((long long)pos * n + b) * C + dir * D + j);
-                g_m[q] = __ldg(a.mask + (long long)pos * n + b);
-                g_r[q] = __ldg(a.r[dir] + o); g_u[q] = __ldg(a.u[dir] + o); g_c[q] = __ldg(a.c[dir] + o); g_p[q] = __ldg(a.p[dir] + o);
-                g_hp[q] = s > 0 ? __ldg(a.cc + ((long long)prev * n + b) * C + dir * D + j) : 0.f;
-                if (a.mean_grad) g_mg[q] = __ldg(a.coef + b) * __ldg(a.mean_grad + (long long)b * C + dir * D + j);
-            }
+        float g_dcc = 0.f, g_m = 1.f, g_r = 0.f, g_u = 0.f, g_c = 0.f, g_p = 0.f, g_hp = 0.f;
+        if (gate_thread) {
+            const long long o = ((long long)pos * n + gb) * D + gj;
+            g_dcc = __ldg(a.dcc + ((long long)pos * n + gb) * C + dir * D + gj);
+            g_m = __ldg(a.mask + (long long)pos * n + gb);
+            g_r = __ldg(a.r[dir] + o); g_u = __ldg(a.u[dir] + o); g_c = __ldg(a.c[dir] + o); g_p = __ldg(a.p[dir] + o);
+            g_hp = s > 0 ? __ldg(a.cc + ((long long)prev * n + gb) * C + dir * D + gj) : 0.f;
         }
-        float acc[kTB][kTC];
-#pragma unroll
-        for (int i = 0; i < kTB; ++i)
-#pragma unroll
-            for (int j = 0; j < kTC; ++j) acc[i][j] = 0.f;
-
+        long long c1 = c0;
         if (s < a.Tx - 1) {
-            const float* gsrc = a.dG[dir] + (long long)nextp * n * D3;        // [n, 3D]
-            const int nch = (D3 + kKC - 1) / kKC;
-            float4 regs[NV];
-            chunk_load<NV>(gsrc, D3, n, D3, 0, BP, tid, nthreads, regs);
-            chunk_store<NV>(buf, BP, tid, nthreads, regs);
+            Frag<kBwdTC> f;
+            f.clear();
+            kslice_product<kBwdTC, kBwdSL, kBwdPF>(a.dG[dir] + (long long)nextp * n * D3, D3, n, D3, Wt, buf + warp * kStageWarp, warp, lane, (int)blockIdx.x, f);
             __syncthreads();
-            for (int ch = 0; ch < nch; ++ch) {
-                const float* cur = buf + (ch & 1) * ring;
-                if (ch + 1 < nch) chunk_load<NV>(gsrc, D3, n, D3, (ch + 1) * kKC, BP, tid, nthreads, regs);
-                if (worker) chunk_fma(cur, Wt, ncolp, BP, ch * kKC, D3, ks, KS, bg, cg, acc);
-                if (ch + 1 < nch) chunk_store<NV>(buf + ((ch + 1) & 1) * ring, BP, tid, nthreads, regs);
-                __syncthreads();
-            }
-            reduce_to_slabs(buf, BP, ncolp, ks, KS, a.NS, bg, cg, worker, acc);
+            c1 = clock64();
+            reduce_to_slabs<kBwdTC, kBwdSL>(buf, a.NS, warp, lane, f);
         }
-#pragma unroll
-        for (int q = 0; q < kPairs; ++q) {
-            const int idx = tid + q * nthreads;
-            if (idx < n * nu) {
-                const int b = idx / nu, uu = idx - b * nu;
-                const int j = j0 + uu;
-                const float m = g_m[q];
-                float dh = g_dcc[q] + carry[q] + m * g_mg[q];
-                if (s < a.Tx - 1) {
-                    const int nsl = KS < a.NS ? KS : a.NS;
-                    for (int sl = 0; sl < nsl; ++sl) dh += buf[((size_t)sl * BP + b) * ncolp + uu];
-                }
-                const float r = g_r[q], uz = g_u[q], c = g_c[q], p = g_p[q], hp = g_hp[q];
-                const float dhn = m * dh;
-                const float du = dhn * (hp - c);
-                const float dc = dhn * (1.f - uz);
-                const float dpc = dc * (1.f - c * c);
-                const float dp = dpc * r;
-                const float dr = dpc * p;
-                const float dgr = dr * r * (1.f - r);
-                const float dgu = du * uz * (1.f - uz);
-                const long long row3 = ((long long)pos * n + b) * D3;
-                a.dG[dir][row3 + j] = dgr; a.dG[dir][row3 + D + j] = dgu; a.dG[dir][row3 + 2 * D + j] = dp;
-                a.dGx[dir][row3 + j] = dgr; a.dGx[dir][row3 + D + j] = dgu; a.dGx[dir][row3 + 2 * D + j] = dpc;
-                carry[q] = (1.f - m) * dh + dhn * uz;
-            }
+        const long long c2 = clock64();
+        if (gate_thread) {
+            const float m = g_m;
+            float dh = g_dcc + carry + m * mg;
+            if (s < a.Tx - 1)
+                for (int sl = 0; sl < nsl; ++sl) dh += buf[(size_t)sl * kBwdSlab + gi];
+            const float r = g_r, uz = g_u, c = g_c, p = g_p, hp = g_hp;
+            const float dhn = m * dh;
+            const float du = dhn * (hp - c);
+            const float dc = dhn * (1.f - uz);
+            const float dpc = dc * (1.f - c * c);
+            const float dp = dpc * r;
+            const float dr = dpc * p;
+            const float dgr = dr * r * (1.f - r);
+            const float dgu = du * uz * (1.f - uz);
+            const long long row3 = ((long long)pos * n + gb) * D3;
+            a.dG[dir][row3 + gj] = dgr; a.dG[dir][row3 + D + gj] = dgu; a.dG[dir][row3 + 2 * D + gj] = dp;
+            a.dGx[dir][row3 + gj] = dgr; a.dGx[dir][row3 + D + gj] = dgu; a.dGx[dir][row3 + 2 * D + gj] = dpc;
+            carry = (1.f - m) * dh + dhn * uz;
         }
+        const long long c3 = clock64();
         if (s > 0) dir_barrier(a.bar + dir, (unsigned)a.P * (unsigned)(a.Tx - s));
+        const long long c4 = clock64();
+        t_comp += c1 - c0; t_red += c2 - c1; t_gate += c3 - c2; t_bar += c4 - c3;
+    }
+    if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        a.dbg[4] = t_comp; a.dbg[5] = t_red; a.dbg[6] = t_gate; a.dbg[7] = t_bar;
     }
 }
 
 struct PersistPlan {
-    int upc_f, P_f, threads_fwd, nv_fwd, ns_fwd; size_t smem_fwd;
-    int upc_b, P_b, threads_bwd, nv_bwd, ns_bwd; size_t smem_bwd;
-    int BP;
+    int upc_f, P_f, ns_fwd; size_t smem_fwd;
+    int upc_b, P_b, ns_bwd; size_t smem_bwd;
     bool ok;
 };
 
 PersistPlan plan(const nats_ctx* ctx, int n, int D) {
     PersistPlan pl;
     memset(&pl, 0, sizeof(pl));
-    if (n < 1 || n > 64 || D < 4 || (D % 4) != 0) return pl;
+    if (n < 1 || n > kBP || D < 8 || (D % 8) != 0) return pl;
     const int per_dir = ctx->num_sms / 2;
     if (per_dir < 1) return pl;
-    int BP = 8;
-    while (BP < n) BP *= 2;                           // power of two: the chunk swizzle XORs float4 column indices
-    pl.BP = BP;
-    const int NBG = BP / kTB;
-    const size_t ring = 2u * kKC * BP;
-    auto shape = [&](int ncolp, int ks_cap, int* threads, int* ns, int* nv) -> bool {
-        const int NCG = ncolp / kTC, grp = NBG * NCG;
-        int ks = kMaxThreads / grp;
-        if (ks > ks_cap) ks = ks_cap;
-        if (ks < 1) return false;
-        int th = ((ks * grp + 31) / 32) * 32;
-        if (th > kMaxThreads) th = (kMaxThreads / 32) * 32;
-        if (th < 128) th = 128;
-        *threads = th;
-        int s = (int)(ring / ((size_t)BP * ncolp));   // reduction slabs live in the idle chunk ring
-        const int KS = th / grp;
-        if (s > KS) s = KS;
-        if (s < 1) return false;
-        *ns = s;
-        *nv = (BP * (kKC / 4) + th - 1) / th;
-        return true;
-    };
-    {   // forward: 3*upc columns per CTA
-        pl.upc_f = (D + per_dir - 1) / per_dir;
-        pl.P_f = (D + pl.upc_f - 1) / pl.upc_f;
-        const int ncolp = (3 * pl.upc_f + 7) & ~7;
-        if (!shape(ncolp, 16, &pl.threads_fwd, &pl.ns_fwd, &pl.nv_fwd)) return pl;
-        const size_t slabs = (size_t)pl.ns_fwd * BP * ncolp;
-        pl.smem_fwd = ((size_t)D * ncolp + (ring > slabs ? ring : slabs)) * sizeof(float);
-        if ((long long)n * pl.upc_f > 2LL * pl.threads_fwd) return pl;
-    }
-    {   // backward: upc columns per CTA (multiple of 8: no padded columns)
-        pl.upc_b = (((D + per_dir - 1) / per_dir) + 7) & ~7;
-        pl.P_b = (D + pl.upc_b - 1) / pl.upc_b;
-        const int ncolp = pl.upc_b;
-        if (!shape(ncolp, 32, &pl.threads_bwd, &pl.ns_bwd, &pl.nv_bwd)) return pl;
-        const size_t slabs = (size_t)pl.ns_bwd * BP * ncolp;
-        pl.smem_bwd = ((size_t)3 * D * ncolp + (ring > slabs ? ring : slabs)) * sizeof(float);
-        if ((long long)n * pl.upc_b > 2LL * pl.threads_bwd) return pl;
-    }
     const size_t lim = (size_t)ctx->max_smem_optin - 1024;
+    {   // forward: 3*upc <= 48 columns per CTA
+        pl.upc_f = (D + per_dir - 1) / per_dir;
+        if (pl.upc_f < 8) pl.upc_f = D < 8 ? D : 8;
+        if (3 * pl.upc_f > kFwdCols) return pl;
+        pl.P_f = (D + pl.upc_f - 1) / pl.upc_f;
+        const size_t w = (size_t)D * kFwdCols;
+        if (w * sizeof(float) + kStageFloats * sizeof(float) > lim) return pl;
+        size_t room = lim / sizeof(float) - w;
+        if (room > 2u * kStageFloats) room = 2u * kStageFloats;           // 32 KB is plenty
+        pl.ns_fwd = (int)(room / kFwdSlab);
+        if (pl.ns_fwd > kWarps) pl.ns_fwd = kWarps;
+        if (pl.ns_fwd < 1) return pl;
+        const size_t slabs = (size_t)pl.ns_fwd * kFwdSlab;
+        pl.smem_fwd = (w + (slabs > (size_t)kStageFloats ? slabs : (size_t)kStageFloats)) * sizeof(float);
+    }
+    {   // backward: upc <= 16 columns per CTA
+        pl.upc_b = kBwdCols;
+        pl.P_b = (D + pl.upc_b - 1) / pl.upc_b;
+        const size_t w = (size_t)3 * D * kBwdCols;
+        if (w * sizeof(float) + kStageFloats * sizeof(float) > lim) return pl;
+        size_t room = lim / sizeof(float) - w;
+        if (room > 2u * kStageFloats) room = 2u * kStageFloats;
+        pl.ns_bwd = (int)(room / kBwdSlab);
+        if (pl.ns_bwd > kWarps) pl.ns_bwd = kWarps;
+        if (pl.ns_bwd < 1) return pl;
+        const size_t slabs = (size_t)pl.ns_bwd * kBwdSlab;
+        pl.smem_bwd = (w + (slabs > (size_t)kStageFloats ? slabs : (size_t)kStageFloats)) * sizeof(float);
+    }
     pl.ok = pl.smem_fwd <= lim && pl.smem_bwd <= lim && 2 * pl.P_f <= ctx->num_sms && 2 * pl.P_b <= ctx->num_sms &&
-            pl.nv_fwd <= 8 && pl.nv_bwd <= 8;
+            n * pl.upc_f <= kThreads && n * pl.upc_b <= kThreads;
     return pl;
 }
 
@@ -467,14 +471,16 @@ void enc_persistent_enable(int on) { g_persist = on; }
 
 int enc_persistent_setup(const nats_ctx* ctx) {
     const int lim = ctx->max_smem_optin - 1024;
-    NATS_CUDA_OK(cudaFuncSetAttribute(enc_persist_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NATS_CUDA_OK(cudaFuncSetAttribute(enc_persist_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NATS_CUDA_OK(cudaFuncSetAttribute(enc_persist_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    NATS_CUDA_OK(cudaFuncSetAttribute(enc_persist_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NATS_CUDA_OK(cudaFuncSetAttribute(enc_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    NATS_CUDA_OK(cudaFuncSetAttribute(enc_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     return 0;
 }
 
-bool enc_persistent_eligible(const nats_ctx* ctx, int n, int D) { return g_persist && plan(ctx, n, D).ok; }
+// g_persist: 0 off, 1 both passes, 2 forward only, 3 backward only
+bool enc_persistent_eligible(const nats_ctx* ctx, int n, int D, int pass) {
+    if (!(g_persist == 1 || (g_persist == 2 && pass == 0) || (g_persist == 3 && pass == 1))) return false;
+    return plan(ctx, n, D).ok;
+}
 
 int enc_persistent_fwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistFwdArgs& g) {
     const PersistPlan pl = plan(ctx, g.n, g.D);
@@ -488,12 +494,11 @@ int enc_persistent_fwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistFwd
     }
     a.mask = g.mask; a.cc = g.cc; a.ctxsum = g.ctxsum; a.bar = g.bar;
     a.dbg = reinterpret_cast<long long*>(g.bar + 16);      // scratch ints after the two counters (debug phase timers)
-    a.Tx = g.Tx; a.n = g.n; a.D = g.D; a.upc = pl.upc_f; a.P = pl.P_f; a.BP = pl.BP; a.NS = pl.ns_fwd;
+    a.Tx = g.Tx; a.n = g.n; a.D = g.D; a.upc = pl.upc_f; a.P = pl.P_f; a.NS = pl.ns_fwd;
     NATS_CUDA_OK(memset_async(st, g.bar, 0, 2 * sizeof(unsigned)));
     ProfScope ps(st, K_ENC_PERSIST_FWD, 2.0 * 2 * g.Tx * (double)g.n * 3.0 * g.D * g.D, 4.0 * 2 * 3.0 * g.D * g.D);
     dim3 grid(pl.P_f, 2);
-    if (pl.nv_fwd <= 4) enc_persist_fwd_kernel<4><<<grid, pl.threads_fwd, pl.smem_fwd, st>>>(a);
-    else enc_persist_fwd_kernel<8><<<grid, pl.threads_fwd, pl.smem_fwd, st>>>(a);
+    enc_persist_fwd_kernel<<<grid, kThreads, pl.smem_fwd, st>>>(a);
     NATS_LAUNCH_OK();
     return 0;
 }
@@ -501,6 +506,7 @@ int enc_persistent_fwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistFwd
 int enc_persistent_bwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistBwdArgs& g) {
     const PersistPlan pl = plan(ctx, g.n, g.D);
     NATS_REQUIRE(pl.ok, "persistent encoder not applicable");
+    NATS_REQUIRE((reinterpret_cast<uintptr_t>(g.dG[0]) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.dG[1]) & 15) == 0, "dG alignment");
     EncPBwd a;
     memset(&a, 0, sizeof(a));
     for (int d = 0; d < 2; ++d) {
@@ -509,12 +515,12 @@ int enc_persistent_bwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistBwd
         a.dG[d] = g.dG[d]; a.dGx[d] = g.dGx[d];
     }
     a.dcc = g.dcc; a.mean_grad = g.mean_grad; a.coef = g.coef; a.mask = g.mask; a.cc = g.cc; a.bar = g.bar;
-    a.Tx = g.Tx; a.n = g.n; a.D = g.D; a.upc = pl.upc_b; a.P = pl.P_b; a.BP = pl.BP; a.NS = pl.ns_bwd;
+    a.dbg = reinterpret_cast<long long*>(g.bar + 16);
+    a.Tx = g.Tx; a.n = g.n; a.D = g.D; a.upc = pl.upc_b; a.P = pl.P_b; a.NS = pl.ns_bwd;
     NATS_CUDA_OK(memset_async(st, g.bar, 0, 2 * sizeof(unsigned)));
     ProfScope ps(st, K_ENC_PERSIST_BWD, 2.0 * 2 * g.Tx * (double)g.n * 3.0 * g.D * g.D, 4.0 * 2 * 3.0 * g.D * g.D);
     dim3 grid(pl.P_b, 2);
-    if (pl.nv_bwd <= 4) enc_persist_bwd_kernel<4><<<grid, pl.threads_bwd, pl.smem_bwd, st>>>(a);
-    else enc_persist_bwd_kernel<8><<<grid, pl.threads_bwd, pl.smem_bwd, st>>>(a);
+    enc_persist_bwd_kernel<<<grid, kThreads, pl.smem_bwd, st>>>(a);
     NATS_LAUNCH_OK();
     return 0;
 }

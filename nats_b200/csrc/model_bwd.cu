@@ -194,7 +194,7 @@ int train_encoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
     const int S = gemm_pick_split(ctx, B, D, D3, 2);
     const long long strideP = 2LL * B * D;
     const bool fused = gru_step_eligible(B, D);
-    const bool persistent = enc_persistent_eligible(ctx, B, D);
+    const bool persistent = enc_persistent_eligible(ctx, B, D, 1);
     if (persistent) {
         EncPersistBwdArgs pa;
         memset(&pa, 0, sizeof(pa));

@@ -27,7 +27,7 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
     const int S = gemm_pick_split(ctx, n, D3, D, 2);
     const int cfg = gemm_step_cfg(n);
     const long long strideP = 2LL * n * D3;
-    if (enc_persistent_eligible(ctx, n, D) && e.step_counters != nullptr) {
+    if (enc_persistent_eligible(ctx, n, D, 0) && e.step_counters != nullptr) {
         // the whole recurrence of both directions in ONE persistent weight-stationary launch (enc_persistent.cu)
         EncPersistFwdArgs pa;
         memset(&pa, 0, sizeof(pa));

@@ -67,14 +67,24 @@ def roofline_of(kernels, workload, peaks_path):
     cls = kernels['classes']
     name = max(cls, key=lambda k: cls[k]['ms_per_step'])
     k = cls[name]
+    # DRAM bytes per launch of that kernel class from the committed `ncu --set full` capture (profiles/ncu_traffic.json)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(peaks_path), 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            t = json.load(f).get(name)
+        if t:
+            traffic, traffic_src = t.get('dram_bytes_per_launch'), t.get('source')
     if name.startswith('gemm'):
         ach = k['TFLOPps']
         return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': tf, 'unit': 'TFLOP/s',
-                'frac': ach / tf if ach else None, 'traffic': None, 'peak_source': which + ' bf16 dense, sustained',
+                'frac': ach / tf if ach else None, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': which + ' bf16 dense, sustained',
                 'share_of_step': k['share'], 'us_per_launch': k['us_per_launch'],
                 'note': 'v1 arithmetic is exact-fp32 FFMA (CUDA cores); the tensor-core ceiling is quoted as the '
                         'bound the GEMM-shaped work must be moved to'}
     ach = k['GBps']
     return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
-            'frac': ach / hbm if ach else None, 'traffic': None, 'peak_source': which + ' copy bandwidth',
+            'frac': ach / hbm if ach else None, 'traffic': traffic, 'traffic_source': traffic_src,
+            'algo_bytes_per_launch': (k['algo_gbytes_per_step'] * 1e9 / k['launches_per_step']) if k['launches_per_step'] else None,
+            'peak_source': which + ' copy bandwidth',
             'share_of_step': k['share'], 'us_per_launch': k['us_per_launch']}

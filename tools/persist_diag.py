@@ -24,8 +24,12 @@ enc(); torch.cuda.synchronize()
 e0.record(); enc(); e1.record(); torch.cuda.synchronize()
 print('encoder fwd total %.3f ms' % e0.elapsed_time(e1))
 ptr = lib.nats_train_ws_view(ctypes.byref(g.dims), Tx, Ty, B, ctypes.c_void_p(p.ws.data_ptr()), b'step_counters')
-if ptr:
-    off = (ptr - p.ws.data_ptr())
+off = (ptr - p.ws.data_ptr())
+def show(name, lo):
     dbg = p.ws[off + 64: off + 64 + 64].view(torch.int64).cpu().numpy()
-    tot = dbg[:4].sum()
-    print('CTA(0,0) cycles per step: first-chunk %.0f  compute %.0f  gates %.0f  barrier %.0f  (total %.0f = %.2f us @1.965GHz)' % tuple(list(dbg[:4] / Tx) + [tot / Tx, tot / Tx / 1965.0]))
+    d = dbg[lo:lo + 4]; tot = d.sum()
+    print('%s CTA(0,0) cycles per step: product %.0f  reduce %.0f  gates %.0f  barrier %.0f  (total %.0f = %.2f us @1.965GHz)' % tuple([name] + list(d / Tx) + [tot / Tx, tot / Tx / 1965.0]))
+show('fwd', 0)
+g.grad_step(b[0], b[1], b[2], b[3], lambda *a, **k: None)
+torch.cuda.synchronize()
+show('bwd', 4)
