@@ -98,6 +98,9 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     if (r == 0) r = gru_step_setup();
     if (r == 0) r = enc_persistent_setup(c);
     enc_persistent_enable(getenv("NATS_PERSISTENT") ? atoi(getenv("NATS_PERSISTENT")) : 0);
+    if (getenv("NATS_GEMM_DBG")) tma_gemm_debug_mode(atoi(getenv("NATS_GEMM_DBG")));
+    if (getenv("NATS_TRACE_GATES")) gates_trace(atoi(getenv("NATS_TRACE_GATES")));
+    if (getenv("NATS_TRACE")) { tma_gemm_trace(atoi(getenv("NATS_TRACE"))); }
     pdl_set(getenv("NATS_PDL") ? atoi(getenv("NATS_PDL")) : 1);
     gru_step_enable(getenv("NATS_FUSED_STEP") ? atoi(getenv("NATS_FUSED_STEP")) : 0);
     gemm_set_tensor_cores(getenv("NATS_TC") ? atoi(getenv("NATS_TC")) : 2);

@@ -124,6 +124,11 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // A kernel launched through launch_pdl() may start while its predecessor in the stream is still running: it calls
 // pdl_trigger() as early as possible (lets ITS dependents launch) and pdl_wait() before the first access to memory that
 // a predecessor may have written or may still read.  Kernels without the attribute keep the ordinary stream order.
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

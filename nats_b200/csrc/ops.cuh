@@ -88,6 +88,9 @@ struct EncPersistBwdArgs {
     const float* r[2]; const float* u[2]; const float* c[2]; const float* p[2];
     float* dG[2]; float* dGx[2]; unsigned* bar; int Tx, n, D;
 };
+void gates_trace(int on);
+void tma_gemm_trace(int on);
+void tma_gemm_debug_mode(int mode);
 bool enc_persistent_eligible(const nats_ctx* ctx, int n, int D, int pass);   // pass: 0 forward, 1 backward
 void enc_persistent_enable(int on);
 int enc_persistent_setup(const nats_ctx* ctx);

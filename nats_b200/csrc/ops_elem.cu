@@ -34,13 +34,23 @@ __global__ void scatter_add_rows_kernel(float* __restrict__ dWemb, const int64_t
 }
 
 // ------------------------------------------------------------------ GRU gates
-struct GateFwdPack { GateFwd g[2]; };
-struct GateBwdPack { GateBwd g[2]; };
+struct GateFwdPack { GateFwd g[2]; int trace; };
+struct GateBwdPack { GateBwd g[2]; int trace; };
+
+static int g_gate_trace = 0;
+static long long g_gate_no = 0;
 
 template <int MODE>
 __global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, int B, int D) {
+#ifdef NATS_TRACE_BUILD
+    const bool tr = pack.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+#else
+    constexpr bool tr = false;
+#endif
+    const unsigned long long t0 = tr ? gtimer() : 0ull;
     pdl_trigger();
     pdl_wait();
+    const unsigned long long t1 = tr ? gtimer() : 0ull;
     const GateFwd& a = pack.g[blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * D) return;
@@ -77,6 +87,9 @@ __global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, i
         a.r[idx] = r; a.u[idx] = u; a.c[idx] = c; a.p[idx] = pp;
     }
     if (a.ctxsum) a.ctxsum[(long long)b * a.ld_ctxsum + j] += m * h;
+#ifdef NATS_TRACE_BUILD
+    if (tr) printf("[trace gates_fwd] start %llu | wait_done +%llu | end +%llu ns\n", t0 % 100000000ull, t1 - t0, gtimer() - t0);
+#endif
 }
 
 __global__ void gru_gates_bwd_kernel(const __grid_constant__ GateBwdPack pack, int B, int D) {
@@ -227,6 +240,7 @@ int gru_gates_fwd(cudaStream_t st, const GateFwd* groups, int ngroups, int B, in
     GateFwdPack pack;
     memset(&pack, 0, sizeof(pack));
     for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
+    if (g_gate_trace) { ++g_gate_no; pack.trace = (g_gate_no >= g_gate_trace - 1 && g_gate_no < g_gate_trace + 4) ? 1 : 0; }
     dim3 grid(cdiv(B * D, 256), ngroups);
     ProfScope ps(st, K_GATES_FWD);
     if (mode == 0) NATS_CUDA_OK(launch_pdl(gru_gates_fwd_kernel<0>, grid, dim3(256), 0, st, pack, B, D));
@@ -308,5 +322,7 @@ int cost_reduce(cudaStream_t st, const float* rowcost, int Ty, int B, float* cos
     NATS_LAUNCH_OK();
     return 0;
 }
+
+void gates_trace(int on) { g_gate_trace = on; g_gate_no = 0; }
 
 }  // namespace nats

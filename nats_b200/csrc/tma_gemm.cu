@@ -48,6 +48,8 @@ struct alignas(64) TmaGroup {
     TmaProblem p[kMaxGroup];
     int zstart[kMaxGroup + 1];
     int count;
+    int trace;           // debug: CTA (0,0,0) prints its phase timestamps (NATS_TRACE)
+    int dbg_mode;        // debug timing experiments (WRONG results): 1 = skip the residual arithmetic, 2 = hi*hi product only
 };
 
 using namespace tc;
@@ -68,6 +70,13 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     __shared__ __align__(8) uint64_t lo_empty[NL];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ unsigned long long tr_s[16];
+#ifdef NATS_TRACE_BUILD
+    const bool tr = grp.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#else
+    constexpr bool tr = false;
+#endif
+    if (tr && threadIdx.x == 0) tr_s[0] = gtimer();
 
     int z = blockIdx.z, g = 0;
     if (grp.count > 1 && z >= grp.zstart[1]) g = 1;
@@ -101,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
+    if (tr && tid == 0) tr_s[1] = gtimer();
     pdl_trigger();                      // dependents may launch now (they block in their own pdl_wait)
 
     if (warp < 8) {
@@ -109,8 +119,10 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
             const int sr = kb % NR, sl = kb % NL;
             mbar_wait(&lo_empty[sl], (uint32_t)(((kb / NL) & 1) ^ 1));      // residual slot drained by the tensor core
             mbar_wait(&tma_full[sr], (uint32_t)((kb / NR) & 1));            // raw tiles landed
+            if (tr && tid == 0 && kb == 0) tr_s[5] = gtimer();
             const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
             const uint32_t lo = smem_base + kLoBase + (uint32_t)sl * kRawStage;
+            if (grp.dbg_mode != 1)
 #pragma unroll
             for (int i = 0; i < (int)(kRawStage / 16 + kSplitThreads - 1) / kSplitThreads; ++i) {
                 const uint32_t q = (uint32_t)(tid + i * kSplitThreads);
@@ -126,6 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&lo_full[sl]);                        // one arrival per warp
         }
+        if (tr && tid == 0) tr_s[6] = gtimer();
     } else {
         if (warp == 8 && lane == 0) {
             // ===================== TMA producer =====================
@@ -144,7 +157,9 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
                     tma_load_3d(raw, mapA, &tma_full[kb], k0, m0, batch);
                 }
             }
+            if (tr) tr_s[2] = gtimer();
             pdl_wait();
+            if (tr) tr_s[3] = gtimer();
             for (int kb = 0; kb < nkb; ++kb) {
                 const int sr = kb % NR;
                 mbar_wait(&raw_empty[sr], (uint32_t)(((kb / NR) & 1) ^ 1));
@@ -176,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
                     tma_load_3d(raw + kABytes, mapB, &tma_full[sr], k0, n0, batch);
                 }
             }
+            if (tr) tr_s[4] = gtimer();
         } else if (warp == 9 && lane == 0) {
             // ===================== MMA issuer =====================
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
@@ -183,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
             for (int kb = 0; kb < nkb; ++kb) {
                 const int sr = kb % NR, sl = kb % NL;
                 mbar_wait(&lo_full[sl], (uint32_t)((kb / NL) & 1));          // implies tma_full[sr] (the residual warps waited on it)
+                if (tr && kb == 0) tr_s[7] = gtimer();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
                 const uint32_t lo = smem_base + kLoBase + (uint32_t)sl * kRawStage;
@@ -195,14 +212,17 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
                     const uint64_t adv_a = (uint64_t)((A_MN ? kk * 1024 : kk * 32) >> 4);
                     const uint64_t adv_b = (uint64_t)((B_MN ? kk * 1024 : kk * 32) >> 4);
                     const int gstep = kb * 4 + kk;
-                    umma_tf32(tmem_d + 3u * BN, a_lo + adv_a, b_raw + adv_b, idesc, gstep != 0 ? 1u : 0u);
-                    umma_tf32(tmem_d + 3u * BN, a_raw + adv_a, b_lo + adv_b, idesc, 1u);
+                    if (grp.dbg_mode != 2) {
+                        umma_tf32(tmem_d + 3u * BN, a_lo + adv_a, b_raw + adv_b, idesc, gstep != 0 ? 1u : 0u);
+                        umma_tf32(tmem_d + 3u * BN, a_raw + adv_a, b_lo + adv_b, idesc, 1u);
+                    }
                     umma_tf32(tmem_d + (uint32_t)(gstep % 3) * BN, a_raw + adv_a, b_raw + adv_b, idesc, gstep >= 3 ? 1u : 0u);
                 }
                 umma_commit(&raw_empty[sr]);                                 // both slots are free once these MMAs retire
                 umma_commit(&lo_empty[sl]);
             }
             umma_commit(&accum_bar);
+            if (tr) tr_s[8] = gtimer();
         }
         __syncwarp();
         // ===================== epilogue (warps 8-11 <-> TMEM lanes 32q..32q+31) =====================
@@ -214,65 +234,100 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
             mbar_wait(&accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        if (tr && warp == 10 && lane == 0) tr_s[9] = gtimer();
         pdl_wait();                     // C may still be read (or accumulated into) by the predecessor
-        const float bias_a = (add_bias && P.bias_on_a && i < P.Ma) ? __ldg(P.bias + i) : 0.f;
+        if (tr && warp == 10 && lane == 0) tr_s[12] = gtimer();
+        // every field of P used below is copied to a local first: P lives in the kernel parameter space behind a
+        // runtime group index, and the unrolled store loop would otherwise re-fetch it per element
+        const int Ma = P.Ma, Nb = P.Nb;
+        const long long c_rs = P.c_rs, c_cs = P.c_cs;
+        const bool accumulate = P.accumulate != 0;
+        const float* bias_n = (add_bias && !P.bias_on_a) ? P.bias : nullptr;
+        const float bias_a = (add_bias && P.bias_on_a && i < Ma) ? __ldg(P.bias + i) : 0.f;
+        const int dbg = grp.dbg_mode;
+        const bool c_vec_ok = (c_cs == 1) && ((c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            if (n0 + c0 >= P.Nb) break;
-            float r[16];
-            if (nkb > 0) {
-                uint32_t t0[16], t1[16], t2[16], t3[16];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= Nb) break;
+            // 32 columns per round: the eight TMEM loads (4 accumulators x 2 halves) are all in flight before the one wait
+            float r[32];
+            if (nkb > 0 && dbg != 4) {
+                uint32_t t0[16], t1[16], t2[16], t3[16], u0[16], u1[16], u2[16], u3[16];
                 const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
                 tmem_ld16(ta, t0);
                 tmem_ld16(ta + BN, t1);
                 tmem_ld16(ta + 2 * BN, t2);
                 tmem_ld16(ta + 3 * BN, t3);
+                tmem_ld16(ta + 16, u0);
+                tmem_ld16(ta + 16 + BN, u1);
+                tmem_ld16(ta + 16 + 2 * BN, u2);
+                tmem_ld16(ta + 16 + 3 * BN, u3);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (tr && warp == 10 && lane == 0) tr_s[11] = gtimer();
 #pragma unroll
-                for (int t = 0; t < 16; ++t)
-                    r[t] = ((__uint_as_float(t0[t]) + __uint_as_float(t1[t])) + __uint_as_float(t2[t])) + __uint_as_float(t3[t]);
+                for (int t = 0; t < 16; ++t) {
+                    r[t] = ((__uint_as_float(t0[t]) + __uint_as_float(t1[t])) + __uint_as_float(t2[t])) + __uint_as_float(t3[t]) + bias_a;
+                    r[16 + t] = ((__uint_as_float(u0[t]) + __uint_as_float(u1[t])) + __uint_as_float(u2[t])) + __uint_as_float(u3[t]) + bias_a;
+                }
             } else {
 #pragma unroll
-                for (int t = 0; t < 16; ++t) r[t] = 0.f;
+                for (int t = 0; t < 32; ++t) r[t] = bias_a;
             }
-            if (i < P.Ma) {
-                float* crow = C + (long long)i * P.c_rs;
-                const bool vec = (P.c_cs == 1) && ((P.c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
-                                 (n0 + c0 + 15 < P.Nb);
-                if (vec) {
+            if (i < Ma && dbg != 3) {
+                const int jb = n0 + c0;
+                const bool full = jb + 31 < Nb;
+                float* cp = C + (long long)i * c_rs + (long long)jb * c_cs;
+                if (full && !accumulate && bias_n == nullptr) {
+                    // the common case (split-K slabs, activations without a column bias): straight stores
+                    if (c_vec_ok) {
 #pragma unroll
-                    for (int t = 0; t < 16; t += 4) {
-                        const int j = n0 + c0 + t;
-                        float4 o = make_float4(r[t] + bias_a, r[t + 1] + bias_a, r[t + 2] + bias_a, r[t + 3] + bias_a);
-                        if (add_bias && !P.bias_on_a) {
-                            o.x += __ldg(P.bias + j); o.y += __ldg(P.bias + j + 1);
-                            o.z += __ldg(P.bias + j + 2); o.w += __ldg(P.bias + j + 3);
+                        for (int t = 0; t < 32; t += 4)
+                            *reinterpret_cast<float4*>(cp + t) = make_float4(r[t], r[t + 1], r[t + 2], r[t + 3]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) cp[(long long)t * c_cs] = r[t];
+                    }
+                } else if (full && c_vec_ok) {
+#pragma unroll
+                    for (int t = 0; t < 32; t += 4) {
+                        float4 o = make_float4(r[t], r[t + 1], r[t + 2], r[t + 3]);
+                        if (bias_n) {
+                            o.x += __ldg(bias_n + jb + t); o.y += __ldg(bias_n + jb + t + 1);
+                            o.z += __ldg(bias_n + jb + t + 2); o.w += __ldg(bias_n + jb + t + 3);
                         }
-                        float4* cp = reinterpret_cast<float4*>(crow + j);
-                        if (P.accumulate) {
-                            const float4 old = *cp;
+                        float4* c4 = reinterpret_cast<float4*>(cp + t);
+                        if (accumulate) {
+                            const float4 old = *c4;
                             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                         }
-                        *cp = o;
+                        *c4 = o;
                     }
                 } else {
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const int j = n0 + c0 + t;
-                        if (j < P.Nb) {
-                            float o = r[t] + bias_a;
-                            if (add_bias && !P.bias_on_a) o += __ldg(P.bias + j);
-                            float* cp = crow + (long long)j * P.c_cs;
-                            if (P.accumulate) o += *cp;
-                            *cp = o;
+#pragma unroll 4
+                    for (int t = 0; t < 32; ++t) {
+                        if (jb + t < Nb) {
+                            float o = r[t];
+                            if (bias_n) o += __ldg(bias_n + jb + t);
+                            float* ce = cp + (long long)t * c_cs;
+                            if (accumulate) o += *ce;
+                            *ce = o;
                         }
                     }
                 }
             }
         }
     }
+    if (tr && warp == 10 && lane == 0) tr_s[10] = gtimer();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+#ifdef NATS_TRACE_BUILD
+    if (tr && tid == 0) {
+        const unsigned long long t0 = tr_s[0];
+        printf("[trace gemm BN=%d nkb=%d] start %llu | setup +%llu | prod: prewait +%llu wait_done +%llu issued +%llu | resid: first_full +%llu done +%llu | mma: first +%llu last_commit +%llu | epi: accum +%llu pdlwait +%llu tmem_ld +%llu stored +%llu | end +%llu ns\n",
+               BN, nkb, t0 % 100000000ull, tr_s[1] - t0, tr_s[2] - t0, tr_s[3] - t0, tr_s[4] - t0, tr_s[5] - t0, tr_s[6] - t0, tr_s[7] - t0,
+               tr_s[8] - t0, tr_s[9] - t0, tr_s[12] - t0, tr_s[11] - t0, tr_s[10] - t0, gtimer() - t0);
+    }
+#endif
     if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
     }
@@ -331,8 +386,17 @@ int get_map(const float* ptr, long long inner, long long outer, long long ld, lo
     return 0;
 }
 
+static int g_trace_on = 0;
+static int g_dbg_mode = 0;
+static long long g_trace_no = 0;
+
 template <int BN, int NR, int NL>
-int launch_bn(cudaStream_t st, const TmaGroup& grp, bool a_mn, bool b_mn, dim3 grid, double flops, double bytes) {
+int launch_bn(cudaStream_t st, TmaGroup& grp, bool a_mn, bool b_mn, dim3 grid, double flops, double bytes) {
+    grp.dbg_mode = g_dbg_mode;
+    if (g_trace_on && BN == 32) {
+        ++g_trace_no;
+        grp.trace = (g_trace_no >= g_trace_on && g_trace_no < g_trace_on + 4) ? 1 : 0;
+    }
     ProfScope ps(st, BN <= 64 ? K_TC_GEMM_SKINNY : K_TC_GEMM, flops, bytes);
     const size_t sm = smem_bytes<BN, NR, NL>();
     cudaError_t le;
@@ -361,6 +425,8 @@ int tma_map_3d(const float* ptr, long long inner, long long outer, long long ld,
     return get_map(ptr, inner, outer, ld, batch, bstride, box_outer, mn_major, out);
 }
 bool tma_available() { return g_encode != nullptr; }
+void tma_gemm_trace(int on) { g_trace_on = on; g_trace_no = 0; }
+void tma_gemm_debug_mode(int mode) { g_dbg_mode = mode; }
 
 int tma_gemm_setup() {
     void* fn = nullptr;
