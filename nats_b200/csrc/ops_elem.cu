@@ -37,6 +37,19 @@ __global__ void scatter_add_rows_kernel(float* __restrict__ dWemb, const int64_t
 struct GateFwdPack { GateFwd g[2]; int trace; };
 struct GateBwdPack { GateBwd g[2]; int trace; };
 
+// Sum of split-K slabs in ascending order with the loads of four slabs in flight at once (a runtime-trip-count loop of
+// load+add pairs would serialise one L2 round trip per slab: the in-order issue stalls on each add).
+__device__ __forceinline__ void load4(const float* __restrict__ p, long long stride, int s0, int n, float (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (s0 + k < n) ? p[(long long)(s0 + k) * stride] : 0.f;
+}
+__device__ __forceinline__ float add4(float acc, const float (&v)[4], int s0, int n) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (s0 + k < n) acc += v[k];
+    return acc;
+}
+
 static int g_gate_trace = 0;
 static long long g_gate_no = 0;
 
@@ -49,38 +62,59 @@ __global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, i
 #endif
     const unsigned long long t0 = tr ? gtimer() : 0ull;
     pdl_trigger();
+    // the kernel parameters (cold constant cache on every launch) and the index arithmetic do not depend on the
+    // predecessor: fetch them while it is still running
+    const GateFwd a = pack.g[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = idx / D, j = idx - b * D;
+    asm volatile("" ::"l"(a.part), "l"(a.xproj), "l"(a.part2), "l"(a.bias), "l"(a.h_prev), "l"(a.mask), "l"(a.h_out), "l"(a.r),
+                 "l"(a.ctxsum), "l"(a.part_stride), "r"(a.nsplit), "r"(a.nsplit2), "r"(j));
     pdl_wait();
     const unsigned long long t1 = tr ? gtimer() : 0ull;
-    const GateFwd& a = pack.g[blockIdx.y];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * D) return;
-    const int b = idx / D, j = idx - b * D;
     const long long row3 = (long long)b * 3 * D;
+    // every load of this element is issued before the first dependent add: one L2 round trip instead of one per slab
+    const float hp = a.h_prev ? a.h_prev[(long long)b * a.ld_hprev + j] : 0.f;
+    const float m = a.mask ? a.mask[b] : 1.f;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+    if (MODE == 0) {
+        const float* x = a.xproj + row3;
+        x0 = x[j]; x1 = x[D + j]; x2 = x[2 * D + j];
+    } else {
+        x0 = __ldg(a.bias + j); x1 = __ldg(a.bias + D + j); x2 = __ldg(a.bias + 2 * D + j);
+    }
     float gr = 0.f, gu = 0.f, pp = 0.f;
-    for (int s = 0; s < a.nsplit; ++s) {
-        const float* ps = a.part + s * a.part_stride + row3;
-        gr += ps[j]; gu += ps[D + j]; pp += ps[2 * D + j];
+    const int nsplit = a.nsplit;
+    const float* ps = a.part + row3 + j;
+    for (int s0 = 0; s0 < nsplit; s0 += 4) {
+        float v0[4], v1[4], v2[4];
+        load4(ps, a.part_stride, s0, nsplit, v0);
+        load4(ps + D, a.part_stride, s0, nsplit, v1);
+        load4(ps + 2 * D, a.part_stride, s0, nsplit, v2);
+        gr = add4(gr, v0, s0, nsplit); gu = add4(gu, v1, s0, nsplit); pp = add4(pp, v2, s0, nsplit);
     }
     float xc;
     if (MODE == 0) {
-        const float* x = a.xproj + row3;
-        gr += x[j]; gu += x[D + j]; xc = x[2 * D + j];
+        gr += x0; gu += x1; xc = x2;
     } else {
         float qr = 0.f, qu = 0.f, qc = 0.f;
-        for (int s = 0; s < a.nsplit2; ++s) {
-            const float* q = a.part2 + s * a.part2_stride + row3;
-            qr += q[j]; qu += q[D + j]; qc += q[2 * D + j];
+        const int nsplit2 = a.nsplit2;
+        const float* qs = a.part2 + row3 + j;
+        for (int s0 = 0; s0 < nsplit2; s0 += 4) {
+            float v0[4], v1[4], v2[4];
+            load4(qs, a.part2_stride, s0, nsplit2, v0);
+            load4(qs + D, a.part2_stride, s0, nsplit2, v1);
+            load4(qs + 2 * D, a.part2_stride, s0, nsplit2, v2);
+            qr = add4(qr, v0, s0, nsplit2); qu = add4(qu, v1, s0, nsplit2); qc = add4(qc, v2, s0, nsplit2);
         }
-        gr += __ldg(a.bias + j) + qr;
-        gu += __ldg(a.bias + D + j) + qu;
-        pp += __ldg(a.bias + 2 * D + j);
+        gr += x0 + qr;
+        gu += x1 + qu;
+        pp += x2;
         xc = qc;
     }
     const float r = sigmoidf_(gr), u = sigmoidf_(gu);
     const float c = tanhf(pp * r + xc);
-    const float hp = a.h_prev ? a.h_prev[(long long)b * a.ld_hprev + j] : 0.f;
     const float hn = u * hp + (1.f - u) * c;
-    const float m = a.mask ? a.mask[b] : 1.f;
     const float h = m * hn + (1.f - m) * hp;
     a.h_out[(long long)b * a.ld_hout + j] = h;
     if (a.r) {
@@ -94,20 +128,39 @@ __global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, i
 
 __global__ void gru_gates_bwd_kernel(const __grid_constant__ GateBwdPack pack, int B, int D) {
     pdl_trigger();
-    pdl_wait();
-    const GateBwd& a = pack.g[blockIdx.y];
+    const GateBwd a = pack.g[blockIdx.y];             // parameters + indices before the dependency wait (see forward)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * D) return;
     const int b = idx / D, j = idx - b * D;
+    asm volatile("" ::"l"(a.part), "l"(a.part2), "l"(a.dh_a), "l"(a.dh_b), "l"(a.h_prev), "l"(a.mask), "l"(a.mean_grad), "l"(a.r),
+                 "l"(a.dG), "l"(a.dGx), "l"(a.dh_elem), "l"(a.part_stride), "r"(a.nsplit), "r"(a.nsplit2), "r"(j));
+    pdl_wait();
+    if (idx >= B * D) return;
     const float m = a.mask ? a.mask[b] : 1.f;
-    float dh = 0.f;
-    if (a.dh_a) dh += a.dh_a[(long long)b * a.ld_a + j];
-    if (a.dh_b) dh += a.dh_b[(long long)b * a.ld_b + j];
-    for (int s = 0; s < a.nsplit; ++s) dh += a.part[s * a.part_stride + (long long)b * a.part_ld + j];
-    for (int s = 0; s < a.nsplit2; ++s) dh += a.part2[s * a.part2_stride + (long long)b * a.part2_ld + j];
-    if (a.mean_grad) dh += m * a.coef[b] * a.mean_grad[(long long)b * a.ld_mean + j];
+    // all loads first (one L2 round trip), then the sums in the fixed order
     const float r = a.r[idx], u = a.u[idx], c = a.c[idx], p = a.p[idx];
     const float hp = a.h_prev ? a.h_prev[(long long)b * a.ld_hprev + j] : 0.f;
+    const float va = a.dh_a ? a.dh_a[(long long)b * a.ld_a + j] : 0.f;
+    const float vb = a.dh_b ? a.dh_b[(long long)b * a.ld_b + j] : 0.f;
+    const float vm = a.mean_grad ? a.coef[b] * a.mean_grad[(long long)b * a.ld_mean + j] : 0.f;
+    float dh = 0.f;
+    if (a.dh_a) dh += va;
+    if (a.dh_b) dh += vb;
+    {
+        const int n1 = a.nsplit, n2 = a.nsplit2;
+        const float* p1 = a.part + (long long)b * a.part_ld + j;
+        const float* p2 = a.part2 + (long long)b * a.part2_ld + j;
+        for (int s0 = 0; s0 < n1; s0 += 4) {
+            float v[4];
+            load4(p1, a.part_stride, s0, n1, v);
+            dh = add4(dh, v, s0, n1);
+        }
+        for (int s0 = 0; s0 < n2; s0 += 4) {
+            float v[4];
+            load4(p2, a.part2_stride, s0, n2, v);
+            dh = add4(dh, v, s0, n2);
+        }
+    }
+    if (a.mean_grad) dh += m * vm;
     const float dhn = m * dh;
     const float du = dhn * (hp - c);
     const float dc = dhn * (1.f - u);

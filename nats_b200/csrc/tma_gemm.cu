@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
     if (tid == 0) {
+        // descriptor fetch off the critical path (the B tiles are requested right after the dependency wait)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(mapB) : "memory");
         for (int s = 0; s < NR; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&raw_empty[s], 1); }
         for (int s = 0; s < NL; ++s) { mbar_init(&lo_full[s], kSplitThreads / 32); mbar_init(&lo_empty[s], 1); }
         mbar_init(&accum_bar, 1);
