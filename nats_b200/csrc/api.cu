@@ -98,6 +98,7 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     if (r == 0) r = gru_step_setup();
     if (r == 0) r = enc_persistent_setup(c);
     enc_persistent_enable(getenv("NATS_PERSISTENT") ? atoi(getenv("NATS_PERSISTENT")) : 0);
+    attention_set_cc_keep(getenv("NATS_CC_KEEP") ? atoi(getenv("NATS_CC_KEEP")) : 0);
     if (getenv("NATS_GEMM_DBG")) tma_gemm_debug_mode(atoi(getenv("NATS_GEMM_DBG")));
     if (getenv("NATS_TRACE_GATES")) gates_trace(atoi(getenv("NATS_TRACE_GATES")));
     if (getenv("NATS_TRACE")) { tma_gemm_trace(atoi(getenv("NATS_TRACE"))); }

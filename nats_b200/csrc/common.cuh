@@ -124,6 +124,19 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // A kernel launched through launch_pdl() may start while its predecessor in the stream is still running: it calls
 // pdl_trigger() as early as possible (lets ITS dependents launch) and pdl_wait() before the first access to memory that
 // a predecessor may have written or may still read.  Kernels without the attribute keep the ordinary stream order.
+// sum_{k<n} p[k*stride] in ascending order, eight loads in flight at a time.  (A runtime-trip-count loop of load+add
+// pairs costs one memory round trip per term: the in-order pipeline stalls on every add.)
+__device__ __forceinline__ float sum_strided(const float* __restrict__ p, long long stride, int n, float acc = 0.f) {
+    for (int k0 = 0; k0 < n; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (k0 + k < n) ? p[(long long)(k0 + k) * stride] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k0 + k < n) acc += v[k];
+    }
+    return acc;
+}
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -133,6 +146,23 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // streaming (read-once) 128-bit load that does not pollute L1
+// L2 eviction policy for the encoder context `cc` (102 MB at config 3, re-streamed by every decoder step): a fraction of
+// its lines is marked evict_last so that it survives in the 126 MB L2 from one pass to the next.  mode: 0 none, 1..4 = 25..100 %
+__device__ __forceinline__ unsigned long long l2_keep_policy(int mode) {
+    unsigned long long pol = 0;
+    if (mode == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.25;" : "=l"(pol));
+    else if (mode == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(pol));
+    else if (mode == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.75;" : "=l"(pol));
+    else if (mode == 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_stream4_hint(const float* p, unsigned long long pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

@@ -251,8 +251,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int nsplit,
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int m = (int)(i / N), n = (int)(i % N);
-        float s = 0.f;
-        for (int k = 0; k < nsplit; ++k) s += part[k * strideP + (long long)m * ldp + n];
+        float s = sum_strided(part + (long long)m * ldp + n, strideP, nsplit);
         if (bias) s += __ldg(bias + n);
         float* o = out + (long long)m * ldo + n;
         if (accumulate) s += *o;

@@ -89,6 +89,7 @@ struct EncPersistBwdArgs {
     float* dG[2]; float* dGx[2]; unsigned* bar; int Tx, n, D;
 };
 void gates_trace(int on);
+void attention_set_cc_keep(int mode);
 void tma_gemm_trace(int on);
 void tma_gemm_debug_mode(int mode);
 bool enc_persistent_eligible(const nats_ctx* ctx, int n, int D, int pass);   // pass: 0 forward, 1 backward
@@ -120,6 +121,7 @@ int cost_reduce(cudaStream_t st, const float* rowcost, int Ty, int B, float* cos
 struct AttFwd {
     const float* pctx; long long pctx_tstride, pctx_bstride;  // element (t,b,a) at pctx[t*ts + b*bs + a]
     const float* cc;   long long cc_tstride, cc_bstride;      // element (t,b,c)
+    int cc_keep;               // L2 evict_last fraction mode for the cc stream (0 none, 1..4 = 25..100 %)
     const float* ps_part; int ps_nsplit; long long ps_stride; // slabs of h1.W_att  [s][n][A]
     float* ps_save;            // [n,A] or NULL
     const float* acc_alpha_in; // [n,Tx]
@@ -140,6 +142,7 @@ int attention_setup(const nats_ctx* ctx);   // one-time kernel attributes
 
 struct AttBwd {
     const float* pctx; const float* cc;           // training layouts [Tx,B,A], [Tx,B,C]
+    int cc_keep;
     const float* dctx_a;                          // [B,C] readout contribution
     const float* dctx_part; int dctx_nsplit; long long dctx_stride;   // slabs [s][B][C] of dG1x.W1cat^T
     const float* dacc_ctx_in; float* dacc_ctx_out; // [B,C]

@@ -9,6 +9,7 @@
 //   (column slices) x (samples) so that >= 2 CTAs per SM keep ~50 KB of bulk copies in flight each.
 // Backward, per decoder step: att_bwd_ctx_kernel, att_bwd_dalpha_kernel (re-streams cc), att_bwd_softmax_kernel.
 #include "ops.cuh"
+#include "tc_common.cuh"
 
 namespace nats {
 
@@ -20,6 +21,7 @@ constexpr int kBwdRows = 16;      // backward kernels: rows of Tx per CTA (more 
 constexpr int kStages = 4;        // context kernel: bulk-copy ring depth
 constexpr int kStageRows = 16;    // rows of cc per stage
 constexpr int kMaxSlice = 256;    // columns per CTA (one per thread)
+constexpr int kScoreAk = 8;       // scores kernel: register path for dim_att <= 256
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -63,8 +65,7 @@ __global__ void __launch_bounds__(kAttThreads) att_scores_kernel(const __grid_co
     float* s_ua = sm + 2 * a.A;
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < a.A; i += blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < a.ps_nsplit; ++k) s += a.ps_part[k * a.ps_stride + (long long)b * a.A + i];
+        const float s = sum_strided(a.ps_part + (long long)b * a.A + i, a.ps_stride, a.ps_nsplit);
         s_ps[i] = s;
         if (blockIdx.x == 0 && a.ps_save) a.ps_save[(long long)b * a.A + i] = s;
         s_dw[i] = __ldg(a.D_wei + i);
@@ -74,6 +75,37 @@ __global__ void __launch_bounds__(kAttThreads) att_scores_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float catt = __ldg(a.c_att);
     const int t_end = min(a.Tx, (int)(blockIdx.x + 1) * kRowsPerCta);
+    if (a.A <= 32 * kScoreAk) {
+        // all loads of a row are issued before the first tanh (a runtime-length load/tanh/add loop serialises one
+        // memory round trip per 32 columns), and the next row's loads are in flight during this row's arithmetic
+        float v[kScoreAk], vn[kScoreAk];
+        float accv = 0.f, accn = 0.f;
+        int t = blockIdx.x * kRowsPerCta + warp;
+        auto fetch = [&](int tt, float (&dst)[kScoreAk], float& av) {
+            if (tt < t_end) {
+                const float* pr = a.pctx + (long long)tt * a.pctx_tstride + (long long)b * a.pctx_bstride;
+                av = a.acc_alpha_in[(long long)b * a.Tx + tt];
+#pragma unroll
+                for (int k = 0; k < kScoreAk; ++k) dst[k] = (lane + 32 * k < a.A) ? __ldg(pr + lane + 32 * k) : 0.f;
+            }
+        };
+        fetch(t, v, accv);
+        for (; t < t_end; t += kAttThreads / 32) {
+            fetch(t + kAttThreads / 32, vn, accn);
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < kScoreAk; ++k) {
+                const int i = lane + 32 * k;
+                if (i < a.A) s += s_ua[i] * tanhf(v[k] + s_ps[i] + accv * s_dw[i]);
+            }
+            s = warp_sum(s);
+            if (lane == 0) a.escore[(long long)b * a.Tx + t] = s + catt;
+#pragma unroll
+            for (int k = 0; k < kScoreAk; ++k) v[k] = vn[k];
+            accv = accn;
+        }
+        return;
+    }
     for (int t = blockIdx.x * kRowsPerCta + warp; t < t_end; t += kAttThreads / 32) {
         const float accv = a.acc_alpha_in[(long long)b * a.Tx + t];
         const float* pr = a.pctx + (long long)t * a.pctx_tstride + (long long)b * a.pctx_bstride;
@@ -85,9 +117,10 @@ __global__ void __launch_bounds__(kAttThreads) att_scores_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------ forward: softmax + context + distraction
-template <bool BULK>
+// BULK: 0 = plain loads, 1 = one bulk copy per row, 2 = one tensor-map tile (16 rows x slice) per stage
+template <int BULK>
 __global__ void __launch_bounds__(kAttThreads) att_context_kernel(const __grid_constant__ AttFwd a, int slice_len,
-                                                                 int slice_pad) {
+                                                                 int slice_pad, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ float red[32];
     const int Txp = (a.Tx + 31) & ~31;
@@ -100,12 +133,34 @@ __global__ void __launch_bounds__(kAttThreads) att_context_kernel(const __grid_c
     const int len = min(slice_len, a.C - c0);
     const float* ccb = a.cc + (long long)b * a.cc_bstride + c0;
     const int nblk = (a.Tx + kStageRows - 1) / kStageRows;
+    const unsigned long long keep_pol = l2_keep_policy(a.cc_keep);
 
     auto issue = [&](int blk) {   // executed by warp 0
         const int stage = blk % kStages;
         const int t0 = blk * kStageRows;
         const int rows = min(kStageRows, a.Tx - t0);
         const int lane = tid & 31;
+        if (BULK == 2) {
+            // the whole stage is ONE TMA instruction: box (slice_pad columns, 1 sample, 16 positions); out-of-range
+            // columns / positions are zero-filled and count towards the transaction bytes
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars[stage], (uint32_t)(kStageRows * slice_pad * 4));
+                if (a.cc_keep > 0) {
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                        ::"r"(smem_u32(s_tile + (long long)stage * kStageRows * slice_pad)), "l"(reinterpret_cast<uint64_t>(&cmap)),
+                        "r"(smem_u32(&bars[stage])), "r"(c0), "r"(b), "r"(t0), "l"(keep_pol)
+                        : "memory");
+                } else {
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                        ::"r"(smem_u32(s_tile + (long long)stage * kStageRows * slice_pad)), "l"(reinterpret_cast<uint64_t>(&cmap)),
+                        "r"(smem_u32(&bars[stage])), "r"(c0), "r"(b), "r"(t0)
+                        : "memory");
+                }
+            }
+            return;
+        }
         if (lane == 0) mbar_arrive_expect_tx(&bars[stage], (uint32_t)(rows * len * 4));
         __syncwarp();
         if (lane < rows)
@@ -116,6 +171,7 @@ __global__ void __launch_bounds__(kAttThreads) att_context_kernel(const __grid_c
     pdl_trigger();
     if (BULK) {
         if (tid == 0) {
+            if (BULK == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&cmap)) : "memory");
             for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
             fence_barrier_init();
         }
@@ -209,7 +265,7 @@ __global__ void att_bwd_ctx_kernel(const __grid_constant__ AttBwd a) {
     const int b = idx / a.C, c = idx - b * a.C;
     const float m = a.ymask ? a.ymask[b] : 1.f;
     float d = a.dctx_a ? a.dctx_a[idx] : 0.f;
-    for (int s = 0; s < a.dctx_nsplit; ++s) d += a.dctx_part[s * a.dctx_stride + idx];
+    d = sum_strided(a.dctx_part + idx, a.dctx_stride, a.dctx_nsplit, d);
     const float dacc = a.dacc_ctx_in[idx];
     d += m * dacc;
     const float cv = a.ctx[idx];
@@ -230,6 +286,8 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_dalpha_kernel(const __gri
     const float m = a.ymask ? a.ymask[b] : 1.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec = ((a.C & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.cc) & 15) == 0);
+    const bool keep = a.cc_keep > 0;
+    const unsigned long long keep_pol = l2_keep_policy(a.cc_keep);
     const int t_end = min(a.Tx, (int)(blockIdx.x + 1) * kBwdRows);
     float dot = 0.f;                                   // this warp's share of sum_t alpha[t] * dalpha[t]
     for (int t = blockIdx.x * kBwdRows + warp; t < t_end; t += kAttThreads / 32) {
@@ -240,7 +298,7 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_dalpha_kernel(const __gri
             const float4* d4 = reinterpret_cast<const float4*>(s_dcraw);
 #pragma unroll 8
             for (int i = lane; i < n4; i += 32) {
-                const float4 v = ldg_stream4(row + 4 * i);
+                const float4 v = keep ? ldg_stream4_hint(row + 4 * i, keep_pol) : ldg_stream4(row + 4 * i);
                 const float4 d = d4[i];
                 s = fmaf(v.x, d.x, s); s = fmaf(v.y, d.y, s); s = fmaf(v.z, d.z, s); s = fmaf(v.w, d.w, s);
             }
@@ -302,18 +360,28 @@ __global__ void __launch_bounds__(kSoftThreads) att_bwd_softmax_kernel(const __g
     const int t_end = min(Tx, (chunk + 1) * kBwdRows);
     for (int t = chunk * kBwdRows + warp; t < t_end; t += kSoftWarps) {
         const long long o = (long long)b * Tx + t;
-        const float de = a.alpha[o] * (a.dalpha[o] - dot);          // masked-softmax backward (nats.py:537-540)
-        const float accv = a.acc_alpha[o];
-        gc += de;
         const long long base = ((long long)t * a.B + b) * A;
+        // every load of the row first (pctx and dpctx may alias as far as the compiler knows: interleaving the
+        // read-modify-write with the loads serialises one memory round trip per 32 columns)
+        float pv[kMaxAk], dv[kMaxAk];
+#pragma unroll
+        for (int k = 0; k < kMaxAk; ++k) {
+            const int i = lane + 32 * k;
+            pv[k] = (i < A) ? __ldg(a.pctx + base + i) : 0.f;
+            dv[k] = (i < A) ? a.dpctx[base + i] : 0.f;
+        }
+        const float al = a.alpha[o], dal = a.dalpha[o];
+        const float accv = a.acc_alpha[o];
+        const float de = al * (dal - dot);                           // masked-softmax backward (nats.py:537-540)
+        gc += de;
         float rowsum = 0.f;
 #pragma unroll
         for (int k = 0; k < kMaxAk; ++k) {
             const int i = lane + 32 * k;
             if (i < A) {
-                const float z = tanhf(a.pctx[base + i] + s_ps[i] + accv * s_dw[i]);
+                const float z = tanhf(pv[k] + s_ps[i] + accv * s_dw[i]);
                 const float dzp = de * s_ua[i] * (1.f - z * z);
-                a.dpctx[base + i] += dzp;
+                a.dpctx[base + i] = dv[k] + dzp;
                 r_dps[k] += dzp;
                 r_gu[k] += de * z;
                 r_gd[k] += accv * dzp;
@@ -351,14 +419,14 @@ __global__ void __launch_bounds__(kSoftThreads) att_bwd_softmax_kernel(const __g
 // dps[b,:] = sum_chunks part ; gatt_part[b,:] += sum_chunks part   (fixed order)
 __global__ void att_bwd_reduce_kernel(const __grid_constant__ AttBwd a, int nchunks) {
     pdl_trigger();
+    const int A = a.A, b = blockIdx.x, W = 3 * A + 1;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;      // one element per thread
+    const float* src = a.soft_part + (long long)b * nchunks * W + i;
     pdl_wait();
-    const int A = a.A, b = blockIdx.x;
-    for (int i = threadIdx.x; i < 3 * A + 1; i += blockDim.x) {
-        float d = 0.f;
-        for (int c = 0; c < nchunks; ++c) d += a.soft_part[((long long)b * nchunks + c) * (3 * A + 1) + i];
-        if (i < A) a.dps[(long long)b * A + i] = d;
-        else a.gatt_part[(long long)b * (2 * A + 1) + (i - A)] += d;     // [dU_att | dD_wei | dc_att]
-    }
+    if (i >= W) return;
+    const float d = sum_strided(src, W, nchunks);
+    if (i < A) a.dps[(long long)b * A + i] = d;
+    else a.gatt_part[(long long)b * (2 * A + 1) + (i - A)] += d;     // [dU_att | dD_wei | dc_att]
 }
 
 inline size_t context_smem(int Tx, bool bulk, int slice_pad) {
@@ -380,11 +448,14 @@ static int set_max_dyn_smem(K kernel, int optin, int* out_limit) {
 }
 
 static int g_att_dyn_limit = 0;
+static int g_cc_keep = 0;
+void attention_set_cc_keep(int mode) { g_cc_keep = mode < 0 ? 0 : (mode > 4 ? 4 : mode); }
 
 int attention_setup(const nats_ctx* ctx) {
     int lim = ctx->max_smem_optin;
-    NATS_TRY(set_max_dyn_smem(att_context_kernel<true>, ctx->max_smem_optin, &lim));
-    NATS_TRY(set_max_dyn_smem(att_context_kernel<false>, ctx->max_smem_optin, &lim));
+    NATS_TRY(set_max_dyn_smem(att_context_kernel<2>, ctx->max_smem_optin, &lim));
+    NATS_TRY(set_max_dyn_smem(att_context_kernel<1>, ctx->max_smem_optin, &lim));
+    NATS_TRY(set_max_dyn_smem(att_context_kernel<0>, ctx->max_smem_optin, &lim));
     NATS_TRY(set_max_dyn_smem(att_bwd_softmax_kernel, ctx->max_smem_optin, &lim));
     NATS_TRY(set_max_dyn_smem(att_bwd_dalpha_kernel, ctx->max_smem_optin, &lim));
     NATS_TRY(set_max_dyn_smem(att_scores_kernel, ctx->max_smem_optin, &lim));
@@ -392,15 +463,18 @@ int attention_setup(const nats_ctx* ctx) {
     return 0;
 }
 
-int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
+int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a_in) {
+    AttFwd a = a_in;
+    a.cc_keep = g_cc_keep;
     NATS_REQUIRE(a.Tx >= 1 && a.n >= 1, "attention shape");
     {
         dim3 grid(cdiv(a.Tx, kRowsPerCta), a.n);
         ProfScope ps(st, K_ATT_SCORES, 0.0, 4.0 * a.Tx * (a.pctx_bstride == 0 ? 1 : a.n) * a.A);
         NATS_CUDA_OK(launch_pdl(att_scores_kernel, grid, dim3(kAttThreads), 3 * a.A * sizeof(float), st, a));
     }
-    // column slices: aim at >= 2 CTAs per SM
-    int target = cdiv(2 * ctx->num_sms, a.n);
+    // column slices: as many CTAs as fit in ONE co-resident wave of 2 CTAs per SM (a partial second wave would run at
+    // the per-CTA latency-bound rate and cost as much as the first)
+    int target = (2 * ctx->num_sms) / a.n;
     if (target < 1) target = 1;
     int slice = cdiv(a.C, target);
     slice = ((slice + 3) / 4) * 4;
@@ -417,12 +491,19 @@ int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a) {
     dim3 grid(nslices, a.n);
     ProfScope ps(st, K_ATT_CONTEXT, 2.0 * a.Tx * a.n * a.C,
                  4.0 * ((double)a.Tx * (a.cc_bstride == 0 ? 1 : a.n) * a.C + 3.0 * a.n * a.Tx + 4.0 * a.n * a.C));
-    if (bulk) NATS_CUDA_OK(launch_pdl(att_context_kernel<true>, grid, dim3(kAttThreads), smem, st, a, slice, slice_pad));
-    else NATS_CUDA_OK(launch_pdl(att_context_kernel<false>, grid, dim3(kAttThreads), smem, st, a, slice, slice_pad));
+    CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    const bool tiled = bulk && tma_available() && a.cc_bstride >= a.C && a.cc_tstride >= (long long)a.n * a.cc_bstride && slice_pad <= 256;
+    if (tiled) NATS_TRY(tma_map_tile3d(a.cc, a.C, a.n, a.Tx, a.cc_bstride, a.cc_tstride, slice_pad, 1, kStageRows, &cmap));
+    if (tiled) NATS_CUDA_OK(launch_pdl(att_context_kernel<2>, grid, dim3(kAttThreads), smem, st, a, slice, slice_pad, cmap));
+    else if (bulk) NATS_CUDA_OK(launch_pdl(att_context_kernel<1>, grid, dim3(kAttThreads), smem, st, a, slice, slice_pad, cmap));
+    else NATS_CUDA_OK(launch_pdl(att_context_kernel<0>, grid, dim3(kAttThreads), smem, st, a, slice, slice_pad, cmap));
     return 0;
 }
 
-int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a) {
+int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a_in) {
+    AttBwd a = a_in;
+    a.cc_keep = g_cc_keep;
     NATS_REQUIRE(a.A <= 32 * kMaxAk, "dim_att > 256 not supported by the attention backward kernel");
     {
         ProfScope ps(st, K_ATT_BWD_CTX);
@@ -440,7 +521,7 @@ int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a) {
         dim3 grid(nchunks, a.B);
         ProfScope ps(st, K_ATT_BWD_SOFTMAX, 0.0, 12.0 * a.Tx * a.B * a.A);
         NATS_CUDA_OK(launch_pdl(att_bwd_softmax_kernel, grid, dim3(kSoftThreads), smem, st, a));
-        NATS_CUDA_OK(launch_pdl(att_bwd_reduce_kernel, dim3(a.B), dim3(128), 0, st, a, nchunks));
+        NATS_CUDA_OK(launch_pdl(att_bwd_reduce_kernel, dim3(a.B, cdiv(3 * a.A + 1, 128)), dim3(128), 0, st, a, nchunks));
     }
     return 0;
 }

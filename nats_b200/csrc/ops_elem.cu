@@ -193,7 +193,7 @@ __global__ void sum_parts_dtanh_kernel(const float* __restrict__ a, const float*
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = a ? a[i] : 0.f;
-    for (int k = 0; k < nsplit; ++k) s += part[k * part_stride + i];
+    s = sum_strided(part + i, part_stride, nsplit, s);
     const float t = y[i];
     dst[i] = s * (1.f - t * t);
 }

@@ -11,6 +11,9 @@ namespace nats {
 int tma_map_3d(const float* ptr, long long inner, long long outer, long long ld, long long batch, long long bstride,
                int box_outer, bool mn_major, CUtensorMap* out);
 bool tma_available();
+// plain (unswizzled) 3-D tile map over fp32: dims (d0 contiguous, d1, d2), strides in elements, box (b0, b1, b2)
+int tma_map_tile3d(const float* ptr, long long d0, long long d1, long long d2, long long stride1, long long stride2, int b0,
+                   int b1, int b2, CUtensorMap* out);
 
 namespace tc {
 

@@ -428,6 +428,32 @@ int tma_map_3d(const float* ptr, long long inner, long long outer, long long ld,
     return get_map(ptr, inner, outer, ld, batch, bstride, box_outer, mn_major, out);
 }
 bool tma_available() { return g_encode != nullptr; }
+
+int tma_map_tile3d(const float* ptr, long long d0, long long d1, long long d2, long long stride1, long long stride2, int b0,
+                   int b1, int b2, CUtensorMap* out) {
+    NATS_REQUIRE(g_encode != nullptr, "tensor maps not available");
+    // cache key reuses MapKey: (inner=d0, outer=d1, ld=stride1, batch=d2, bstride=stride2, box_outer=b0*65536+b1*256+b2, mn=2)
+    MapKey key{ptr, d0, d1, stride1, d2, stride2, b0 * 65536 + b1 * 256 + b2, 2};
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    if (g_maps.size() > (1u << 16)) g_maps.clear();
+    cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t gstr[2] = {(cuuint64_t)stride1 * 4, (cuuint64_t)stride2 * 4};
+    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (tile3d) failed (%d): ptr=%p dims=%lld,%lld,%lld strides=%lld,%lld box=%d,%d,%d", (int)r, ptr, d0,
+                  d1, d2, stride1, stride2, b0, b1, b2);
+        return 1;
+    }
+    g_maps.emplace(key, m);
+    *out = m;
+    return 0;
+}
 void tma_gemm_trace(int on) { g_trace_on = on; g_trace_no = 0; }
 void tma_gemm_debug_mode(int mode) { g_dbg_mode = mode; }
 
