@@ -167,6 +167,79 @@ def _cpu_reference_run(w, steps, warmup, sample_B=8):
                 % (sample_B, w['B'], w['Tx'], w['Ty'], len(times)), cost=float(cost))
 
 
+def extra_regions(nats, _lib, eng, graph, plan, tparams, opts, w, tokens_per_step):
+    """SURVEY 8(d) side regions on one GPU (the headline `value` is R2, the train step):
+    R1 decoder forward = gru_cond_layer scan + readout + NLL on a precomputed context (nats.py:737-770), device-timed;
+    R3 beam step = gen_sample at beam 10, src_len 800, all three distraction penalties on, host-timed per step."""
+    import ctypes
+    import torch
+    lib = eng.lib
+    Tx, Ty, B = plan.shape
+    vp = ctypes.c_void_p
+    D = ctypes.byref(graph.dims)
+    F, XM, Y, YM = vp(tparams.flat.data_ptr()), vp(plan.xm.data_ptr()), vp(plan.y.data_ptr()), vp(plan.ym.data_ptr())
+    WS, C = vp(plan.ws.data_ptr()), vp(plan.cost.data_ptr())
+
+    def r1():
+        _lib.check(lib.nats_decoder_scan_fwd(eng.ctx, eng.stream(), D, F, Y, XM, YM, Tx, Ty, B, WS, plan.ws_bytes), 'scan')
+        _lib.check(lib.nats_readout_nll_fwd(eng.ctx, eng.stream(), D, F, Y, YM, Tx, Ty, B, WS, plan.ws_bytes, C), 'readout')
+    r1()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        r1()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    Dm, A, Cc = w['dim'], w['dim_att'], 2 * w['dim']
+    step_bytes = 4.0 * (Tx * B * (Cc + A) + (12 * Dm * Dm + Dm * A) + B * (10 * Dm + 3 * Cc + 4 * Tx))   # SURVEY 8(d)
+    peaks = {}
+    if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')):
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    out = {'R1_decoder_forward': {
+        'value': tokens_per_step / (ms * 1e-3), 'unit': 'tokens/s', 'ms': ms, 'us_per_decoder_step': 1e3 * ms / Ty,
+        'algo_bytes_per_step': step_bytes, 'achieved_GBps': step_bytes * Ty / (ms * 1e-3) / 1e9,
+        'frac_of_hbm_peak': step_bytes * Ty / (ms * 1e-3) / 1e9 / hbm,
+        'how': 'nats_decoder_scan_fwd + nats_readout_nll_fwd in one CUDA graph, CUDA events, %d replays' % n}}
+
+    # R3: beam search, no hypothesis may finish (EOS logit pushed down), restored afterwards
+    rng = np.random.RandomState(4321)
+    xs = rng.randint(2, w['n_words'], size=(800,)).tolist() + [0]
+    x = np.array(xs, dtype='int64').reshape(-1, 1)
+    f_init, f_next = nats.build_sampler(tparams, opts, None)
+    bsave = tparams['ff_logit_b'].get_value()
+    bmod = bsave.copy()
+    bmod[0] = -1e9
+    tparams['ff_logit_b'].set_value(bmod)
+    try:
+        steps = 20
+        nats.gen_sample(tparams, f_init, f_next, x, opts, None, 10, 4, False, False, True, 1.0, 1.0, 1.0)     # warm
+        torch.cuda.synchronize()
+        t0 = time.time()
+        nats.gen_sample(tparams, f_init, f_next, x, opts, None, 10, steps, False, False, True, 1.0, 1.0, 1.0)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        t1 = time.time()
+        f_init(x)
+        torch.cuda.synchronize()
+        t_init = time.time() - t1
+    finally:
+        tparams['ff_logit_b'].set_value(bsave)
+    out['R3_beam_step'] = {'value': (dt - t_init) / steps * 1e3, 'unit': 'ms per beam step (k=10, src_len=800, 3 penalties)',
+                           'f_init_ms': t_init * 1e3, 'steps': steps, 'hyp_tokens_per_s': 10 * steps / (dt - t_init),
+                           'how': 'gen_sample wall clock incl. host bookkeeping, minus one f_init'}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -176,6 +249,7 @@ def main():
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--probe-steps', type=int, default=2, help='eager steps with per-kernel CUDA-event timing')
+    ap.add_argument('--no-regions', action='store_true', help='skip the R1 (decoder forward) / R3 (beam step) side measurements')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
@@ -299,6 +373,13 @@ def main():
             torch.distributed.destroy_process_group()
         return 0
 
+    regions = None
+    if world == 1 and args.workload == 'c3' and not args.no_regions:
+        try:
+            regions = extra_regions(nats, _lib, eng, graph, plan, tparams, opts, w, tokens_per_step)
+        except Exception as e:       # diagnostics only
+            regions = {'error': repr(e)}
+
     total_tokens = tokens_per_step * max(world, 1) * K
     value_ms = dev_ms if dev_ms is not None else e2e_ms
     line = {
@@ -308,7 +389,7 @@ def main():
         'e2e': {'value': total_tokens / (e2e_ms * 1e-3), 'unit': 'tokens/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / K},
         'gpu_launches': None, 'abi_calls_timed': abi_calls,
-        'clocks': clocks, 'roofline': roofline, 'kernels': kernels,
+        'clocks': clocks, 'roofline': roofline, 'regions': regions, 'kernels': kernels,
         'cost_first_last': [costs[0], costs[-1]],
     }
     if kernels and isinstance(kernels, dict) and 'launches_per_step' in kernels:

@@ -165,6 +165,13 @@ int nats_beam_distraction_scores(nats_ctx_t* ctx, void* stream,
                                  float kl_factor, float ctx_factor, float state_factor,
                                  float* scratch, float* out);
 
+/* replaces: the full argsort over live_k*|V| candidate scores of nats.py:997-999.  Penalties and hypothesis scores are
+ * constant per row, so the global best (k - dead_k) candidates are among each row's (k - dead_k) most probable words:
+ * out_p[i, 0:k] / out_idx[i, 0:k] = the k largest probs[i, :] in descending order (ties: lower index first; -1 pads);
+ * mask_unk != 0 treats entry 1 as 1e-20 (nats.py:975, use_unk=False). */
+int nats_beam_topk(nats_ctx_t* ctx, void* stream, const float* probs /* [n, n_words] */, int n, int n_words, int k,
+                   int mask_unk, float* out_p /* [n,k] */, int32_t* out_idx /* [n,k] */);
+
 /* replaces: the history copies of nats.py:1015-1023: for every new hypothesis j (parent[j] = trans index)
  * dst[j, 0:hist_len] = src[parent[j], 0:hist_len]; dst[j, hist_len] = cur[parent[j]].  dim = row width. */
 int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, float* dst, const float* cur,

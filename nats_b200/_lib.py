@@ -57,6 +57,7 @@ SIGNATURES = {
     'nats_rmsprop_update': (c_int, [c_void_p, _P, c_int64, _P, _P, _P, _P, _P]),
     'nats_beam_distraction_scores': (c_int, [c_void_p, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                              _P, _P, _P, c_float, c_float, c_float, _P, _P]),
+    'nats_beam_topk': (c_int, [c_void_p, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     'nats_beam_reorder_append': (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int]),
     'nats_debug_gemm': (c_int, [c_void_p, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, c_int,
                                 _P, c_int, c_int, c_int, c_int64, c_int64, c_int64]),

@@ -469,6 +469,12 @@ int nats_beam_distraction_scores(nats_ctx_t* ctx, void* stream, const float* his
                                    hist_len, live_k, Tx, C, D, cur_alpha, cur_ctx, cur_state, kl_factor, ctx_factor,
                                    state_factor, scratch, out);
 }
+int nats_beam_topk(nats_ctx_t* ctx, void* stream, const float* probs, int n, int n_words, int k, int mask_unk,
+                   float* out_p, int32_t* out_idx) {
+    (void)ctx;
+    return beam_topk(reinterpret_cast<cudaStream_t>(stream), probs, n, n_words, k, mask_unk, out_p, out_idx);
+}
+
 int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, float* dst, const float* cur,
                              const int32_t* parent, int n_new, int len_cap, int hist_len, int dim) {
     (void)ctx;

@@ -190,6 +190,8 @@ int beam_distraction_scores(cudaStream_t st, const float* hist_alpha, const floa
                             int len_cap, int hist_len, int live_k, int Tx, int C, int D, const float* cur_alpha,
                             const float* cur_ctx, const float* cur_state, float kl, float cf, float sf,
                             float* scratch, float* out);
+// per row the K largest probabilities (descending; ties by ascending index); entry 1 counts as 1e-20 when mask_unk
+int beam_topk(cudaStream_t st, const float* probs, int n, int V, int K, int mask_unk, float* out_p, int32_t* out_idx);
 int beam_reorder_append(cudaStream_t st, const float* src, float* dst, const float* cur, const int32_t* parent,
                         int n_new, int len_cap, int hist_len, int dim);
 

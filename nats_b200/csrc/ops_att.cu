@@ -18,7 +18,7 @@ namespace {
 constexpr int kAttThreads = 256;
 constexpr int kRowsPerCta = 32;   // scores kernel: rows of Tx per CTA
 constexpr int kBwdRows = 16;      // backward kernels: rows of Tx per CTA (more CTAs in flight for the cc re-stream)
-constexpr int kStages = 4;        // context kernel: bulk-copy ring depth
+constexpr int kStages = 4;        // context kernel: tile ring depth (7 stages measured no faster)
 constexpr int kStageRows = 16;    // rows of cc per stage
 constexpr int kMaxSlice = 256;    // columns per CTA (one per thread)
 constexpr int kScoreAk = 8;       // scores kernel: register path for dim_att <= 256
@@ -296,11 +296,22 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_dalpha_kernel(const __gri
         if (vec) {
             const int n4 = a.C >> 2;
             const float4* d4 = reinterpret_cast<const float4*>(s_dcraw);
-#pragma unroll 8
-            for (int i = lane; i < n4; i += 32) {
-                const float4 v = keep ? ldg_stream4_hint(row + 4 * i, keep_pol) : ldg_stream4(row + 4 * i);
-                const float4 d = d4[i];
-                s = fmaf(v.x, d.x, s); s = fmaf(v.y, d.y, s); s = fmaf(v.z, d.z, s); s = fmaf(v.w, d.w, s);
+            // eight 16-byte loads per lane in flight before the first dependent FMA (the accumulation order is unchanged)
+            for (int i0 = lane; i0 < n4; i0 += 32 * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + 32 * k;
+                    if (i < n4) v[k] = keep ? ldg_stream4_hint(row + 4 * i, keep_pol) : ldg_stream4(row + 4 * i);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + 32 * k;
+                    if (i < n4) {
+                        const float4 d = d4[i];
+                        s = fmaf(v[k].x, d.x, s); s = fmaf(v[k].y, d.y, s); s = fmaf(v[k].z, d.z, s); s = fmaf(v[k].w, d.w, s);
+                    }
+                }
             }
         } else {
             for (int i = lane; i < a.C; i += 32) s = fmaf(__ldg(row + i), s_dcraw[i], s);

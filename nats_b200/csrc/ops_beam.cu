@@ -101,4 +101,68 @@ int beam_reorder_append(cudaStream_t st, const float* src, float* dst, const flo
     return 0;
 }
 
+
+namespace {
+
+// One CTA per hypothesis row.  Round r selects the largest probability that comes strictly after the previous pick in
+// the total order (value descending, index ascending): no marking, no copy of the row, any vocabulary size; the row
+// (120 KB at |V| = 30000) is re-read from L1/L2 K times.
+__global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict__ probs, int V, int K, int mask_unk,
+                                                        float* __restrict__ out_p, int32_t* __restrict__ out_idx) {
+    __shared__ float s_v[8];
+    __shared__ int s_i[8];
+    __shared__ float s_pv;
+    __shared__ int s_pi;
+    const float* row = probs + (long long)blockIdx.x * V;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float pv = INFINITY;
+    int pi = -1;
+    for (int r = 0; r < K; ++r) {
+        float bv = -1.f;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < V; i += 256) {
+            float v = __ldg(row + i);
+            if (mask_unk && i == 1) v = 1e-20f;                        // nats.py:975: next_p[:,1] = 1e-20
+            if (!(v == v)) v = 0.f;                                      // NaN never wins
+            const bool after = (v < pv) || (v == pv && i > pi);
+            if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            float v = s_v[0];
+            int i = s_i[0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w)
+                if (s_v[w] > v || (s_v[w] == v && s_i[w] < i)) { v = s_v[w]; i = s_i[w]; }
+            if (i == 0x7fffffff) { v = 0.f; i = -1; }                    // fewer than K candidates
+            out_p[(long long)blockIdx.x * K + r] = v;
+            out_idx[(long long)blockIdx.x * K + r] = i;
+            s_pv = v; s_pi = i;
+        }
+        __syncthreads();
+        pv = s_pv; pi = s_pi;
+        if (pi < 0) {                                                    // exhausted: fill the rest
+            if (tid == 0)
+                for (int q = r + 1; q < K; ++q) { out_p[(long long)blockIdx.x * K + q] = 0.f; out_idx[(long long)blockIdx.x * K + q] = -1; }
+            break;
+        }
+    }
+}
+
+}  // namespace
+
+int beam_topk(cudaStream_t st, const float* probs, int n, int V, int K, int mask_unk, float* out_p, int32_t* out_idx) {
+    NATS_REQUIRE(n >= 1 && V >= 1 && K >= 1, "beam_topk shape");
+    beam_topk_kernel<<<n, 256, 0, st>>>(probs, V, K, mask_unk, out_p, out_idx);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace nats

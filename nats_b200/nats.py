@@ -643,6 +643,82 @@ class _CtxHandle(object):
         return bool(numpy.array_equal(a, numpy.broadcast_to(h[self.probe_t], a.shape)))
 
 
+class DeviceArray(object):
+    """What f_next returns in place of a host ndarray: a device tensor that is copied to the host the first time
+    NumPy needs its values (`numpy.log(a)`, `a[0]`, `a[:, 1] = v` ...).  Row selection with an index list
+    (`a[parents]`) and `.copy()` stay on the device, so gen_sample can hand states and accumulators straight back
+    to f_next without a host round trip."""
+    __array_priority__ = 1000
+
+    def __init__(self, tensor):
+        self._t = tensor
+        self._h = None
+        self._dirty = False
+
+    shape = property(lambda self: tuple(self._t.shape))
+    ndim = property(lambda self: self._t.dim())
+    dtype = property(lambda self: numpy.dtype(str(self._t.dtype).replace('torch.', '')))
+    size = property(lambda self: int(self._t.numel()))
+
+    def __len__(self):
+        return int(self._t.shape[0])
+
+    def host(self):
+        if self._h is None:
+            self._h = self._t.cpu().numpy()
+        return self._h
+
+    def tensor(self):
+        """the device tensor (re-uploaded if the host copy was written to)"""
+        if self._dirty:
+            self._t.copy_(self._t.new_tensor(self._h))
+            self._dirty = False
+        return self._t
+
+    def __array__(self, dtype=None, copy=None):
+        h = self.host()
+        return h if dtype is None else h.astype(dtype, copy=False)
+
+    def __getitem__(self, idx):
+        rows = isinstance(idx, (list, numpy.ndarray)) and numpy.asarray(idx).ndim == 1 and \
+            numpy.asarray(idx).dtype.kind in 'iu'
+        if rows and not self._dirty:
+            import torch
+            ii = torch.as_tensor(numpy.asarray(idx, dtype='int64'), device=self._t.device)
+            return DeviceArray(self._t.index_select(0, ii))
+        return self.host()[idx]
+
+    def __setitem__(self, idx, value):
+        self.host()[idx] = value
+        self._dirty = True
+
+    def copy(self):
+        if self._h is not None:
+            return self._h.copy()
+        return DeviceArray(self._t.clone())
+
+    def argmax(self, *a, **k):
+        return self.host().argmax(*a, **k)
+
+    def flatten(self):
+        return self.host().flatten()
+
+    def __repr__(self):
+        return 'DeviceArray(%r)' % (self.host(),)
+
+
+def _binop(name):
+    def f(self, other):
+        return getattr(self.host(), name)(numpy.asarray(other))
+    return f
+
+
+for _n in ('__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__', '__truediv__', '__rtruediv__',
+           '__lt__', '__le__', '__gt__', '__ge__', '__eq__', '__ne__'):
+    setattr(DeviceArray, _n, _binop(_n))
+DeviceArray.__hash__ = None
+
+
 def build_sampler(tparams, options, trng=None):
     """-> f_init, f_next with the reference signatures (nats.py:817, 869-871)."""
     eng = tparams.engine
@@ -689,7 +765,10 @@ def build_sampler(tparams, options, trng=None):
                 raise ValueError('ctx has %d columns, y has %d' % (ctx_d.shape[1], n))
             cts, cbs, pts, pbs = n * C, C, 0, 0
             pptr = ctypes.c_void_p(0)
-        up = lambda a, shp: torch.from_numpy(numpy.ascontiguousarray(a, dtype='float32').reshape(shp)).to(eng.device)
+        def up(a, shp):
+            if isinstance(a, DeviceArray):                    # came out of a previous f_next: already on the device
+                return a.tensor().reshape(shp).contiguous()
+            return torch.from_numpy(numpy.ascontiguousarray(a, dtype='float32').reshape(shp)).to(eng.device)
         yd = torch.from_numpy(y).to(eng.device)
         st_d, ac_d, aa_d = up(init_state, (n, D)), up(acc_ctx, (n, C)), up(acc_alpha, (n, Tx))
         ws, nbytes = ws_for(Tx, n)
@@ -705,12 +784,24 @@ def build_sampler(tparams, options, trng=None):
             'nats_sampler_next')
         eng.launches += 1
         counter[0] += 1
-        f_next.last_device = dict(alpha=alphaT, ctx=ctxs, state=state_o)
-        return [probs.cpu().numpy(), sample.cpu().numpy(), state_o.cpu().numpy(), alphaT.cpu().numpy(),
-                ctxs.cpu().numpy(), acc_ctx_o.cpu().numpy(), acc_alpha_o.cpu().numpy()]
+        f_next.last_device = dict(alpha=alphaT, ctx=ctxs, state=state_o, probs=probs)
+        # same seven outputs in the same order (nats.py:869-870); each becomes a host array on first NumPy access
+        return [DeviceArray(probs), DeviceArray(sample), DeviceArray(state_o), DeviceArray(alphaT), DeviceArray(ctxs),
+                DeviceArray(acc_ctx_o), DeviceArray(acc_alpha_o)]
+
+    def topk(probs_dev, kk, mask_unk):
+        """(p [n,kk] float32, idx [n,kk] int32) host arrays: the kk most probable words of every row"""
+        n = int(probs_dev.shape[0])
+        tp = torch.empty((n, kk), dtype=torch.float32, device=eng.device)
+        ti = torch.empty((n, kk), dtype=torch.int32, device=eng.device)
+        _lib.check(eng.lib.nats_beam_topk(eng.ctx, eng.stream(), _ptr(probs_dev), n, int(probs_dev.shape[1]), kk,
+                                          1 if mask_unk else 0, _ptr(tp), _ptr(ti)), 'nats_beam_topk')
+        eng.launches += 1
+        return tp.cpu().numpy(), ti.cpu().numpy()
 
     f_next.last_device = None
     f_next.engine = eng
+    f_next.topk = topk
     return f_init, f_next
 
 
@@ -820,22 +911,43 @@ def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, s
 
         dev = getattr(f_next, 'last_device', None) or {}
         cur = (dev.get('alpha', dec_alphas), dev.get('ctx', ctxs), dev.get('state', next_state))
-        if not use_unk:
-            next_p[:, 1] = 1e-20
-        cand_scores = hyp_scores[:, None] - numpy.log(next_p)
-        cand_flat = cand_scores.flatten()
         n_keep = k - dead_k
-        if distract and ii > 0:
-            pen = scorer.penalties(cur[0], cur[1], cur[2], live_k, kl_factor, ctx_factor, state_factor)
-            ranked = (cand_scores + pen[0][:, None] + pen[1][:, None] + pen[2][:, None]).flatten()
-            ranks_flat = ranked.argsort()[:n_keep]
+        topk = getattr(f_next, 'topk', None)
+        if topk is not None and dev.get('probs') is not None and isinstance(next_p, DeviceArray) and \
+                next_p._h is None and n_keep <= next_p.shape[1]:
+            # Hypothesis scores and penalties are constant per row, so the best n_keep candidates overall are among
+            # each row's n_keep most probable words: select those on the device (nats_beam_topk) instead of sorting
+            # all live_k*|V| scores on the host; same ranking rule, same un-penalised stored cost (nats.py:997-1004).
+            top_p, top_i = topk(dev['probs'], n_keep, not use_unk)
+            with numpy.errstate(divide='ignore'):
+                cand_scores = hyp_scores[:, None] - numpy.log(top_p)
+            cand_flat = cand_scores.flatten()
+            if distract and ii > 0:
+                pen = scorer.penalties(cur[0], cur[1], cur[2], live_k, kl_factor, ctx_factor, state_factor)
+                ranked = (cand_scores + pen[0][:, None] + pen[1][:, None] + pen[2][:, None]).flatten()
+            else:
+                ranked = cand_flat
+            ranked = numpy.where(top_i.flatten() < 0, numpy.float32(numpy.inf), ranked)
+            ranks_flat = ranked.argsort(kind='stable')[:n_keep]
+            trans_indices = ranks_flat // n_keep
+            word_indices = top_i.flatten()[ranks_flat].astype('int64')
+            costs = cand_flat[ranks_flat]
         else:
-            ranks_flat = cand_flat.argsort()[:n_keep]
+            if not use_unk:
+                next_p[:, 1] = 1e-20
+            cand_scores = hyp_scores[:, None] - numpy.log(next_p)
+            cand_flat = cand_scores.flatten()
+            if distract and ii > 0:
+                pen = scorer.penalties(cur[0], cur[1], cur[2], live_k, kl_factor, ctx_factor, state_factor)
+                ranked = (cand_scores + pen[0][:, None] + pen[1][:, None] + pen[2][:, None]).flatten()
+                ranks_flat = ranked.argsort()[:n_keep]
+            else:
+                ranks_flat = cand_flat.argsort()[:n_keep]
 
-        voc_size = next_p.shape[1]
-        trans_indices = ranks_flat // voc_size
-        word_indices = ranks_flat % voc_size
-        costs = cand_flat[ranks_flat]
+            voc_size = next_p.shape[1]
+            trans_indices = ranks_flat // voc_size
+            word_indices = ranks_flat % voc_size
+            costs = cand_flat[ranks_flat]
 
         survivors = []                    # (parent index, word, cost) of the hypotheses that stay alive
         for ti, wi, ci in zip(trans_indices, word_indices, costs):
@@ -862,7 +974,7 @@ def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, s
         hyp_scores = numpy.array([s[2] for s in survivors], dtype='float32')
         hyp_dec_alphas = [s[3] for s in survivors]
         next_w = numpy.array([w[-1] for w in hyp_samples], dtype='int64')
-        next_state = next_state[parents].copy()
+        next_state = next_state[parents].copy()      # DeviceArray: a device-side row gather
         acc_ctx = acc_ctx[parents].copy()
         acc_alpha = acc_alpha[parents].copy()
 

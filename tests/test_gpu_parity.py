@@ -269,6 +269,78 @@ def test_beam_search_matches_oracle_and_golden(N):
     assert list(map(int, s1)) == list(map(int, s2))
 
 
+def test_beam_topk_matches_numpy(N):
+    """nats_beam_topk: per row the k largest probabilities, descending, ties by ascending index, entry 1 -> 1e-20
+    when use_unk is off (nats.py:975) -- the selection that replaces the host argsort of nats.py:997-999."""
+    import ctypes
+    import torch
+    from nats_b200 import _lib
+    eng = N.get_engine()
+    rng = np.random.RandomState(5)
+    for (n, V, K) in [(7, 1000, 5), (3, 30011, 10), (2, 6, 6), (1, 3, 5)]:
+        p = rng.rand(n, V).astype('float32')
+        p[:, 1] = 2.0                                   # the unk entry is the largest unless masked
+        if V > 40:
+            p[0, 17] = p[0, 33] = 1.5                   # a tie: lower index first
+        pd = torch.from_numpy(p).to(eng.device)
+        for mask in (0, 1):
+            op = torch.empty((n, K), dtype=torch.float32, device=eng.device)
+            oi = torch.empty((n, K), dtype=torch.int32, device=eng.device)
+            _lib.check(eng.lib.nats_beam_topk(eng.ctx, eng.stream(), ctypes.c_void_p(pd.data_ptr()), n, V, K, mask,
+                                              ctypes.c_void_p(op.data_ptr()), ctypes.c_void_p(oi.data_ptr())), 'topk')
+            gp, gi = op.cpu().numpy(), oi.cpu().numpy()
+            q = p.copy()
+            if mask:
+                q[:, 1] = 1e-20
+            for r in range(n):
+                order = np.lexsort((np.arange(V), -q[r]))[:K]        # value descending, index ascending
+                kk = min(K, V)
+                assert list(gi[r, :kk]) == list(order[:kk]), (n, V, K, mask, r)
+                np.testing.assert_array_equal(gp[r, :kk], q[r, order[:kk]])
+                assert all(gi[r, kk:] == -1)
+
+
+def test_sampler_outputs_are_lazy_device_arrays(N):
+    """f_next returns the seven outputs of nats.py:869-870 as DeviceArray: NumPy sees ordinary arrays, row selection
+    stays on the device and can be fed back to f_next unchanged."""
+    zt = np.load(os.path.join(GOLD, 'train_toy.npz'))
+    V, W, D, A = [int(v) for v in zt['opt_dims']]
+    opts = toy_options(D=D, W=W, A=A, V=V)
+    names = list(O.init_params(opts).keys())
+    P32 = O.cast_params(O.OrderedDict((k, zt['p_' + k]) for k in names), 'float32')
+    tparams = N.init_tparams(P32)
+    f_init, f_next = N.build_sampler(tparams, opts)
+    x = np.array([[3], [5], [7], [0]], dtype='int64')
+    st, ctx = f_init(x)
+    k = 3
+    y = -np.ones((1,), 'int64')
+    out = f_next(y, ctx, st, np.zeros((1, 2 * D), 'float32'), np.zeros((1, 4), 'float32'))
+    assert all(isinstance(o, N.DeviceArray) for o in out)
+    assert out[0].shape == (1, V) and out[0].dtype == np.float32 and out[1].dtype == np.int64
+    p_host = np.asarray(out[0])
+    np.testing.assert_allclose(p_host.sum(1), 1.0, rtol=1e-5)
+    # grow to k hypotheses by device-side row selection, then compare with the same call on host copies
+    par = [0] * k
+    y2 = np.array([4, 5, 6], 'int64')
+    dev_in = (out[2][par].copy(), out[5][par].copy(), out[6][par].copy())
+    assert all(isinstance(a, N.DeviceArray) for a in dev_in)
+    host_in = tuple(np.asarray(o)[par].copy() for o in (out[2], out[5], out[6]))
+    ctx_k = np.tile(ctx, [k, 1])
+    a = f_next(y2, ctx_k, *dev_in)
+    b = f_next(y2, ctx_k, *host_in)
+    for i, (u, v) in enumerate(zip(a, b)):
+        if i != 1:                      # the multinomial draw advances its counter at every call
+            np.testing.assert_array_equal(np.asarray(u), np.asarray(v))
+    # writes go to the host copy and are honoured when the array is passed back
+    s_mod = out[2][par].copy()
+    s_mod[:, 0] = 0.25
+    hm = host_in[0].copy()
+    hm[:, 0] = 0.25
+    c = f_next(y2, ctx_k, s_mod, dev_in[1], dev_in[2])
+    d = f_next(y2, ctx_k, hm, host_in[1], host_in[2])
+    np.testing.assert_array_equal(np.asarray(c[0]), np.asarray(d[0]))
+
+
 def test_full_size_properties(N):
     """BASELINE config 2 shape (Tx=120, Ty=20, D=500, V=4000, B=64 -> here B=16 to keep the oracle out): size-
     independent properties only: alpha rows sum to 1, acc_alpha row sums = #valid steps, padding invariance of the
