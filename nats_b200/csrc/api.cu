@@ -99,6 +99,7 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     if (r == 0) r = enc_persistent_setup(c);
     enc_persistent_enable(getenv("NATS_PERSISTENT") ? atoi(getenv("NATS_PERSISTENT")) : 0);
     attention_set_cc_keep(getenv("NATS_CC_KEEP") ? atoi(getenv("NATS_CC_KEEP")) : 0);
+    tma_gemm_set_ts(getenv("NATS_TS") ? atoi(getenv("NATS_TS")) : 1);
     if (getenv("NATS_GEMM_DBG")) tma_gemm_debug_mode(atoi(getenv("NATS_GEMM_DBG")));
     if (getenv("NATS_TRACE_GATES")) gates_trace(atoi(getenv("NATS_TRACE_GATES")));
     if (getenv("NATS_TRACE")) { tma_gemm_trace(atoi(getenv("NATS_TRACE"))); }
@@ -190,9 +191,13 @@ int nats_debug_gemm(nats_ctx_t* ctx, void* stream, int path, int transA, int tra
     if (splitk > 1) gemm_set_split(p, splitk, (long long)M * ldc);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (path == 1) return tc_gemm_launch(st, &p, 1, transA != 0, transB != 0);
-    if (path == 2) {
+    if (path == 2 || path == 3) {        // 3 = TMA-fed with the 128-row operand in tensor memory (skinny shapes)
         NATS_REQUIRE(tma_gemm_eligible(&p, 1), "operands not TMA-compatible (alignment)");
-        return tma_gemm_launch(st, &p, 1, transA != 0, transB != 0);
+        const int keep_ts = tma_gemm_get_ts();
+        tma_gemm_set_ts(path == 3 ? 1 : 0);
+        const int r = tma_gemm_launch(st, &p, 1, transA != 0, transB != 0);
+        tma_gemm_set_ts(keep_ts);
+        return r;
     }
     const int keep = gemm_get_tensor_cores();
     gemm_set_tensor_cores(0);

@@ -92,6 +92,8 @@ void gates_trace(int on);
 void attention_set_cc_keep(int mode);
 void tma_gemm_trace(int on);
 void tma_gemm_debug_mode(int mode);
+void tma_gemm_set_ts(int on);
+int tma_gemm_get_ts();
 bool enc_persistent_eligible(const nats_ctx* ctx, int n, int D, int pass);   // pass: 0 forward, 1 backward
 void enc_persistent_enable(int on);
 int enc_persistent_setup(const nats_ctx* ctx);

@@ -336,6 +336,301 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TS variant for the skinny products (BN <= 64): the 128-row operand (the weights) is fed to the tensor core from
+// TENSOR MEMORY instead of shared memory.  The SS kernel above moves ~120 KB through the 128 B/clk shared-memory port
+// per 16 KB weight tile (TMA write, residual read+write, three UMMA operand reads) and is bound by it; here the eight
+// split warps read the raw tile ONCE and write both halves  hi = trunc_tf32(x),  lo = x - hi  into TMEM with
+// tcgen05.st (lane = row m, column = k), and the three MMAs of a k-step read A from TMEM: 56 KB per tile.
+//   raw stage (shared, NR deep): [A_raw 16 KB | B_raw | B_lo]      A stage (TMEM, NL deep): [hi 32 cols | lo 32 cols]
+template <int BN, int NR, int NL, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_constant__ TmaGroup grp) {
+    constexpr uint32_t kABytes = 128 * 128, kBBytes = BN * 128;
+    constexpr uint32_t kRawStage = kABytes + 2 * kBBytes;
+    // accumulators: NACC rotating [hi*hi | hi*lo] pairs (2*BN columns each, one N-stacked MMA) + one lo*hi (BN columns).
+    // The tensor core spends the same ~69 cycles on an M128 x N<=128 x K8 step whatever N is, so stacking the two
+    // products that share A_hi along N turns three MMAs per k-step into two.
+    constexpr uint32_t NACC = BN <= 32 ? 3 : 2;
+    constexpr uint32_t kAccCols = NACC * 2 * BN + BN;
+    constexpr uint32_t kTmemCols = (kAccCols + NL * 64 <= 128) ? 128 : ((kAccCols + NL * 64 <= 256) ? 256 : 512);
+    static_assert(kAccCols + NL * 64 <= 512, "tensor memory budget");
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t tma_full[NR];
+    __shared__ __align__(8) uint64_t raw_empty[NR];
+    __shared__ __align__(8) uint64_t a_full[NL];
+    __shared__ __align__(8) uint64_t a_empty[NL];
+    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ unsigned long long tr_s[16];
+#ifdef NATS_TRACE_BUILD
+    const bool tr = grp.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#else
+    constexpr bool tr = false;
+#endif
+    if (tr && threadIdx.x == 0) tr_s[0] = gtimer();
+
+    int z = blockIdx.z, g = 0;
+    if (grp.count > 1 && z >= grp.zstart[1]) g = 1;
+    const TmaProblem& P = grp.p[g];
+    const CUtensorMap* mapA = &grp.mapA[g];
+    const CUtensorMap* mapB = &grp.mapB[g];
+    z -= grp.zstart[g];
+    const int split = z % P.splitk, batch = z / P.splitk;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+    if (m0 >= P.Ma || n0 >= P.Nb) return;
+
+    const int kbeg = split * P.kchunk;
+    const int kend = min(P.K, kbeg + P.kchunk);
+    const int nkb = (kend > kbeg) ? (kend - kbeg + kBlockK - 1) / kBlockK : 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(mapB) : "memory");
+        for (int s = 0; s < NR; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&raw_empty[s], 1); }
+        for (int s = 0; s < NL; ++s) { mbar_init(&a_full[s], kSplitThreads / 32); mbar_init(&a_empty[s], 1); }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+    const uint32_t tmem_a0 = tmem_d + kAccCols;
+    if (tr && tid == 0) tr_s[1] = gtimer();
+    pdl_trigger();
+
+    if (warp < 8) {
+        // ===================== split pass: raw A tile -> (hi, lo) in tensor memory; raw B tile -> B_lo in shared =====
+        const int q = warp & 3, h = warp >> 2;          // TMEM lane quadrant of this warp / which 16 of the 32 k
+        const int m = 32 * q + lane;                    // row of the 128-row tile handled by this thread
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int sr = kb % NR, sl = kb % NL;
+            mbar_wait(&a_empty[sl], (uint32_t)(((kb / NL) & 1) ^ 1));       // the MMAs that read this TMEM stage retired
+            mbar_wait(&tma_full[sr], (uint32_t)((kb / NR) & 1));            // raw tiles landed
+            if (tr && tid == 0 && kb == 0) tr_s[5] = gtimer();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
+            float v[16];
+            if (!A_MN) {        // K-major: row m = 128 B, 16-byte chunks XOR (m & 7)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t addr = raw + (uint32_t)m * 128u + (uint32_t)((((4 * h + c) ^ (m & 7))) << 4);
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3])
+                                 : "r"(addr));
+                }
+            } else {            // MN-major (SW128_32B): 32-row blocks of 4096 B, k rows of 128 B, 32-byte chunks XOR (k & 3)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int k = 16 * h + j;
+                    const uint32_t addr = raw + (uint32_t)(m >> 5) * 4096u + (uint32_t)k * 128u +
+                                          (uint32_t)(((((m & 31) >> 3) ^ (k & 3))) << 5) + (uint32_t)((m & 7) << 2);
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[j]) : "r"(addr));
+                }
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                hi[j] = __float_as_uint(v[j]) & 0xFFFFE000u;
+                lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));
+            }
+            const uint32_t ta = tmem_a0 + ((uint32_t)(32 * q) << 16) + (uint32_t)(sl * 64 + 16 * h);
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 32, lo);
+            // B: lo = raw - trunc(raw), same stage, next to the raw tile
+#pragma unroll
+            for (int i = 0; i < (int)(kBBytes / 16 + kSplitThreads - 1) / kSplitThreads; ++i) {
+                const uint32_t e = (uint32_t)(tid + i * kSplitThreads);
+                if (e < kBBytes / 16) {
+                    float4 b;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(raw + kABytes + e * 16u));
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(raw + kABytes + kBBytes + e * 16u), "f"(resid(b.x)),
+                                 "f"(resid(b.y)), "f"(resid(b.z)), "f"(resid(b.w))
+                                 : "memory");
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[sl]);
+            if (tr && tid == 0 && kb == 0) tr_s[13] = gtimer();
+        }
+        if (tr && tid == 0) tr_s[6] = gtimer();
+    } else {
+        if (warp == 8 && lane == 0) {
+            // ===================== TMA producer (as in the SS kernel) =====================
+            const int npre = P.a_static ? min(nkb, NR) : 0;
+            for (int kb = 0; kb < npre; ++kb) {
+                const uint32_t raw = smem_base + (uint32_t)kb * kRawStage;
+                const int k0 = kbeg + kb * kBlockK;
+                mbar_expect_tx_only(&tma_full[kb], kABytes);
+                if (A_MN) {
+#pragma unroll
+                    for (int bi = 0; bi < 4; ++bi) tma_load_3d(raw + bi * 4096, mapA, &tma_full[kb], m0 + 32 * bi, k0, batch);
+                } else {
+                    tma_load_3d(raw, mapA, &tma_full[kb], k0, m0, batch);
+                }
+            }
+            if (tr) tr_s[2] = gtimer();
+            pdl_wait();
+            if (tr) tr_s[3] = gtimer();
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int sr = kb % NR;
+                mbar_wait(&raw_empty[sr], (uint32_t)(((kb / NR) & 1) ^ 1));
+                const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
+                const int k0 = kbeg + kb * kBlockK;
+                if (kb < npre) {
+                    mbar_expect_tx(&tma_full[sr], kBBytes);
+                } else {
+                    mbar_expect_tx(&tma_full[sr], kABytes + kBBytes);
+                    if (A_MN) {
+#pragma unroll
+                        for (int bi = 0; bi < 4; ++bi) tma_load_3d(raw + bi * 4096, mapA, &tma_full[sr], m0 + 32 * bi, k0, batch);
+                    } else {
+                        tma_load_3d(raw, mapA, &tma_full[sr], k0, m0, batch);
+                    }
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int bi = 0; bi < BN / 32; ++bi)
+                        tma_load_3d(raw + kABytes + bi * 4096, mapB, &tma_full[sr], n0 + 32 * bi, k0, batch);
+                } else {
+                    tma_load_3d(raw + kABytes, mapB, &tma_full[sr], k0, n0, batch);
+                }
+            }
+        } else if (warp == 9 && lane == 0) {
+            // ===================== MMA issuer: A from tensor memory (always K-major there), B from shared =============
+            const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((128u >> 4) << 24);
+            const uint32_t idesc1 = idesc_base | ((uint32_t)(BN >> 3) << 17);            // N = BN
+            const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * BN) >> 3) << 17);      // N = 2*BN: [B_raw | B_lo]
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int sr = kb % NR, sl = kb % NL;
+                mbar_wait(&a_full[sl], (uint32_t)((kb / NL) & 1));
+                if (tr && kb == 0) tr_s[7] = gtimer();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
+                const uint64_t b_raw = B_MN ? desc_mnmajor(raw + kABytes) : desc_kmajor(raw + kABytes);   // B_lo follows contiguously
+                const uint32_t a_hi = tmem_a0 + (uint32_t)(sl * 64), a_lo = a_hi + 32;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t adv_b = (uint64_t)((B_MN ? kk * 1024 : kk * 32) >> 4);
+                    const int gstep = kb * 4 + kk;
+                    umma_tf32_ts(tmem_d + NACC * 2u * BN, a_lo + 8u * kk, b_raw + adv_b, idesc1, gstep != 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_d + (uint32_t)(gstep % NACC) * 2u * BN, a_hi + 8u * kk, b_raw + adv_b, idesc2,
+                                 gstep >= (int)NACC ? 1u : 0u);
+                }
+                umma_commit(&raw_empty[sr]);
+                umma_commit(&a_empty[sl]);
+            }
+            umma_commit(&accum_bar);
+            if (tr) tr_s[8] = gtimer();
+        }
+        __syncwarp();
+        // ===================== epilogue (identical to the SS kernel) =====================
+        const int q = warp - 8;
+        const int i = m0 + q * 32 + lane;
+        float* __restrict__ C = P.C + (long long)batch * P.sC + (long long)split * P.strideP;
+        const bool add_bias = (P.bias != nullptr) && (split == 0);
+        if (nkb > 0) {
+            mbar_wait(&accum_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        if (tr && warp == 10 && lane == 0) tr_s[9] = gtimer();
+        pdl_wait();
+        const int Ma = P.Ma, Nb = P.Nb;
+        const long long c_rs = P.c_rs, c_cs = P.c_cs;
+        const bool accumulate = P.accumulate != 0;
+        const float* bias_n = (add_bias && !P.bias_on_a) ? P.bias : nullptr;
+        const float bias_a = (add_bias && P.bias_on_a && i < Ma) ? __ldg(P.bias + i) : 0.f;
+        const bool c_vec_ok = (c_cs == 1) && ((c_rs & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= Nb) break;
+            float r[32];
+            if (nkb > 0) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {            // 16 columns at a time: 2*NACC + 1 TMEM loads in flight
+                    uint32_t t[2 * NACC + 1][16];
+                    const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 16 * hh);
+#pragma unroll
+                    for (int a = 0; a < (int)NACC; ++a) {
+                        tmem_ld16(ta + a * 2 * BN, t[2 * a]);              // hi*hi
+                        tmem_ld16(ta + a * 2 * BN + BN, t[2 * a + 1]);     // hi*lo
+                    }
+                    tmem_ld16(ta + NACC * 2 * BN, t[2 * NACC]);            // lo*hi
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        float main_sum = __uint_as_float(t[0][e]);
+#pragma unroll
+                        for (int a = 1; a < (int)NACC; ++a) main_sum += __uint_as_float(t[2 * a][e]);
+                        float cross = __uint_as_float(t[2 * NACC][e]);
+#pragma unroll
+                        for (int a = 0; a < (int)NACC; ++a) cross += __uint_as_float(t[2 * a + 1][e]);
+                        r[16 * hh + e] = (main_sum + cross) + bias_a;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) r[t] = bias_a;
+            }
+            if (i < Ma) {
+                const int jb = n0 + c0;
+                const bool full = jb + 31 < Nb;
+                float* cp = C + (long long)i * c_rs + (long long)jb * c_cs;
+                if (full && !accumulate && bias_n == nullptr) {
+                    if (c_vec_ok) {
+#pragma unroll
+                        for (int t = 0; t < 32; t += 4)
+                            *reinterpret_cast<float4*>(cp + t) = make_float4(r[t], r[t + 1], r[t + 2], r[t + 3]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) cp[(long long)t * c_cs] = r[t];
+                    }
+                } else {
+#pragma unroll 4
+                    for (int t = 0; t < 32; ++t) {
+                        if (jb + t < Nb) {
+                            float o = r[t];
+                            if (bias_n) o += __ldg(bias_n + jb + t);
+                            float* ce = cp + (long long)t * c_cs;
+                            if (accumulate) o += *ce;
+                            *ce = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (tr && warp == 10 && lane == 0) tr_s[10] = gtimer();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+#ifdef NATS_TRACE_BUILD
+    if (tr && tid == 0) {
+        const unsigned long long t0 = tr_s[0];
+        printf("[trace ts-gemm BN=%d nkb=%d] start %llu | setup +%llu | prod: prewait +%llu wait_done +%llu | split: first_full +%llu first_done +%llu all_done +%llu | mma: first +%llu last_commit +%llu | epi: accum +%llu stored +%llu | end +%llu ns\n",
+               BN, nkb, t0 % 100000000ull, tr_s[1] - t0, tr_s[2] - t0, tr_s[3] - t0, tr_s[5] - t0, tr_s[13] - t0, tr_s[6] - t0, tr_s[7] - t0,
+               tr_s[8] - t0, tr_s[9] - t0, tr_s[10] - t0, gtimer() - t0);
+    }
+#endif
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int BN, int NR>
+constexpr size_t ts_smem_bytes() { return (size_t)NR * (128 * 128 + 2 * BN * 128) + 1024; }
+
 template <int BN, int NR, int NL>
 constexpr size_t smem_bytes() { return (size_t)(NR + NL) * (128 * 128 + BN * 128) + 1024; }
 
@@ -390,6 +685,7 @@ int get_map(const float* ptr, long long inner, long long outer, long long ld, lo
 }
 
 static int g_trace_on = 0;
+static int g_ts_mode = 1;        // 1: skinny products (BN <= 64) read the 128-row operand from tensor memory
 static int g_dbg_mode = 0;
 static long long g_trace_no = 0;
 
@@ -401,6 +697,19 @@ int launch_bn(cudaStream_t st, TmaGroup& grp, bool a_mn, bool b_mn, dim3 grid, d
         grp.trace = (g_trace_no >= g_trace_on && g_trace_no < g_trace_on + 4) ? 1 : 0;
     }
     ProfScope ps(st, BN <= 64 ? K_TC_GEMM_SKINNY : K_TC_GEMM, flops, bytes);
+    if constexpr (BN <= 64) {
+        if (g_ts_mode) {
+            constexpr int TNR = BN == 32 ? 8 : 6, TNL = BN == 32 ? 4 : 3;
+            const size_t tsm = ts_smem_bytes<BN, TNR>();
+            cudaError_t e;
+            if (!a_mn && !b_mn) e = launch_pdl(tma_gemm_ts_kernel<BN, TNR, TNL, false, false>, grid, dim3(kThreads), tsm, st, grp);
+            else if (!a_mn && b_mn) e = launch_pdl(tma_gemm_ts_kernel<BN, TNR, TNL, false, true>, grid, dim3(kThreads), tsm, st, grp);
+            else if (a_mn && !b_mn) e = launch_pdl(tma_gemm_ts_kernel<BN, TNR, TNL, true, false>, grid, dim3(kThreads), tsm, st, grp);
+            else e = launch_pdl(tma_gemm_ts_kernel<BN, TNR, TNL, true, true>, grid, dim3(kThreads), tsm, st, grp);
+            NATS_CUDA_OK(e);
+            return 0;
+        }
+    }
     const size_t sm = smem_bytes<BN, NR, NL>();
     cudaError_t le;
     if (!a_mn && !b_mn) le = launch_pdl(tma_gemm_kernel<BN, NR, NL, false, false>, grid, dim3(kThreads), sm, st, grp);
@@ -418,6 +727,14 @@ int set_attrs() {
     NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, NR, NL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, NR, NL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_kernel<BN, NR, NL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    if constexpr (BN <= 64) {
+        constexpr int TNR = BN == 32 ? 8 : 6, TNL = BN == 32 ? 4 : 3;
+        const int tsm = (int)ts_smem_bytes<BN, TNR>();
+        NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_ts_kernel<BN, TNR, TNL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+        NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_ts_kernel<BN, TNR, TNL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+        NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_ts_kernel<BN, TNR, TNL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+        NATS_CUDA_OK(cudaFuncSetAttribute(tma_gemm_ts_kernel<BN, TNR, TNL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+    }
     return 0;
 }
 
@@ -456,6 +773,8 @@ int tma_map_tile3d(const float* ptr, long long d0, long long d1, long long d2, l
 }
 void tma_gemm_trace(int on) { g_trace_on = on; g_trace_no = 0; }
 void tma_gemm_debug_mode(int mode) { g_dbg_mode = mode; }
+void tma_gemm_set_ts(int on) { g_ts_mode = on; }
+int tma_gemm_get_ts() { return g_ts_mode; }
 
 int tma_gemm_setup() {
     void* fn = nullptr;
