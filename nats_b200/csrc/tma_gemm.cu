@@ -357,9 +357,12 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
 
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t tma_full[NR];
-    __shared__ __align__(8) uint64_t raw_empty[NR];
+    // One tcgen05.commit per TWO k-blocks (a commit costs the issuing thread ~120 cycles, an MMA ~50): k-block j is known to
+    // have retired when barrier done[(j|1) % NR] completes its ((j|1) / NR)-th phase.  Both the TMA producer (shared stage
+    // j % NR is free) and the split warps (tensor-memory stage j % NL is free) wait on it.
+    static_assert(NR % 2 == 0 && NL <= NR, "ring depths");
+    __shared__ __align__(8) uint64_t done[NR];
     __shared__ __align__(8) uint64_t a_full[NL];
-    __shared__ __align__(8) uint64_t a_empty[NL];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ unsigned long long tr_s[16];
@@ -389,8 +392,8 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(mapB) : "memory");
-        for (int s = 0; s < NR; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&raw_empty[s], 1); }
-        for (int s = 0; s < NL; ++s) { mbar_init(&a_full[s], kSplitThreads / 32); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < NR; ++s) { mbar_init(&tma_full[s], 1); mbar_init(&done[s], 1); }
+        for (int s = 0; s < NL; ++s) mbar_init(&a_full[s], kSplitThreads / 32);
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -414,7 +417,10 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
         const int m = 32 * q + lane;                    // row of the 128-row tile handled by this thread
         for (int kb = 0; kb < nkb; ++kb) {
             const int sr = kb % NR, sl = kb % NL;
-            mbar_wait(&a_empty[sl], (uint32_t)(((kb / NL) & 1) ^ 1));       // the MMAs that read this TMEM stage retired
+            if (kb >= NL) {                                                 // the MMAs that read this TMEM stage retired
+                const int c = (kb - NL) | 1;
+                mbar_wait(&done[c % NR], (uint32_t)((c / NR) & 1));
+            }
             mbar_wait(&tma_full[sr], (uint32_t)((kb / NR) & 1));            // raw tiles landed
             if (tr && tid == 0 && kb == 0) tr_s[5] = gtimer();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -486,7 +492,10 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
             if (tr) tr_s[3] = gtimer();
             for (int kb = 0; kb < nkb; ++kb) {
                 const int sr = kb % NR;
-                mbar_wait(&raw_empty[sr], (uint32_t)(((kb / NR) & 1) ^ 1));
+                if (kb >= NR) {
+                    const int c = (kb - NR) | 1;
+                    mbar_wait(&done[c % NR], (uint32_t)((c / NR) & 1));
+                }
                 const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
                 const int k0 = kbeg + kb * kBlockK;
                 if (kb < npre) {
@@ -529,8 +538,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
                     umma_tf32_ts(tmem_d + (uint32_t)(gstep % NACC) * 2u * BN, a_hi + 8u * kk, b_raw + adv_b, idesc2,
                                  gstep >= (int)NACC ? 1u : 0u);
                 }
-                umma_commit(&raw_empty[sr]);
-                umma_commit(&a_empty[sl]);
+                if (kb & 1) umma_commit(&done[kb % NR]);
             }
             umma_commit(&accum_bar);
             if (tr) tr_s[8] = gtimer();

@@ -64,8 +64,69 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int iters, int nacc, long
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
+
+// the k-block body of the N-stacked TS kernel: [fence] + 4 x (N=BN lo*raw, N=2BN hi*[raw|lo]) + ncommit commits
+__global__ void __launch_bounds__(128, 1) kblock_probe(int BN, int kblocks, int ncommit, int fence, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t dummy[2];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&dummy[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&dummy[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t ib = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+        const uint32_t id1 = ib | ((uint32_t)(BN >> 3) << 17), id2 = ib | ((uint32_t)((2 * BN) >> 3) << 17);
+        const uint64_t db = desc_kmajor(base + 16384);
+        const uint32_t a_hi = tmem + 448, a_lo = tmem + 480;
+        const long long t0 = clock64();
+        for (int kb = 0; kb < kblocks; ++kb) {
+            if (fence) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                             ::"r"(tmem + 6 * BN), "r"(a_lo + 8u * kk), "l"(db + (uint64_t)(2 * kk)), "r"(id1), "r"(1u) : "memory");
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                             ::"r"(tmem + (uint32_t)(kk % 3) * 2 * BN), "r"(a_hi + 8u * kk), "l"(db + (uint64_t)(2 * kk)), "r"(id2), "r"(1u) : "memory");
+            }
+            for (int c = 0; c < ncommit; ++c)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[c])) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        uint32_t ok;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        } while (!ok);
+        if (blockIdx.x == 0) out[1] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
 int main() {
     long long* out; cudaMallocManaged(&out, 16);
+    {
+        const int sm2 = 16384 + 32768 + 1024;
+        cudaFuncSetAttribute(kblock_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
+        for (int nc = 0; nc <= 2; ++nc)
+            for (int fe = 0; fe <= 1; ++fe) {
+                kblock_probe<<<148, 128, sm2>>>(32, 400, nc, fe, out); cudaDeviceSynchronize();
+                printf("TS k-block body (BN=32: 4 x [N32 + N64]), %d commit(s), fence %d: %7.1f clk per k-block  %s\n", nc, fe, (double)out[1] / 400,
+                       cudaGetErrorString(cudaGetLastError()));
+            }
+    }
     const int smem = 16384 + 32768 + 1024, iters = 4800;
     cudaFuncSetAttribute(probe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(probe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
