@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int iters, int nacc, long
 }
 
 // the k-block body of the N-stacked TS kernel: [fence] + 4 x (N=BN lo*raw, N=2BN hi*[raw|lo]) + ncommit commits
-__global__ void __launch_bounds__(128, 1) kblock_probe(int BN, int kblocks, int ncommit, int fence, long long* out) {
+__global__ void __launch_bounds__(128, 1) kblock_probe(int BN, int kblocks, int ncommit, int fence, long long* out, int st_traffic = 0) {
+    __shared__ volatile int stop_flag;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(8) uint64_t dummy[2];
@@ -86,6 +87,21 @@ __global__ void __launch_bounds__(128, 1) kblock_probe(int BN, int kblocks, int 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) stop_flag = 0;
+    __syncthreads();
+    if (st_traffic && threadIdx.x >= 32) {          // warps 1-3: tcgen05.st into columns 256..383 of their lane quadrants, like the split warps
+        const uint32_t q = threadIdx.x >> 5;
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = threadIdx.x + i;
+        int it = 0;
+        while (!stop_flag) {
+            const uint32_t ta = tmem + ((q * 32u) << 16) + 256u + (uint32_t)((it & 7) * 16);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(ta), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+            if ((++it & (st_traffic - 1)) == 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
     if (threadIdx.x == 0) {
         const uint32_t ib = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
         const uint32_t id1 = ib | ((uint32_t)(BN >> 3) << 17), id2 = ib | ((uint32_t)((2 * BN) >> 3) << 17);
@@ -110,6 +126,7 @@ __global__ void __launch_bounds__(128, 1) kblock_probe(int BN, int kblocks, int 
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
         } while (!ok);
         if (blockIdx.x == 0) out[1] = clock64() - t0;
+        stop_flag = 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -120,6 +137,11 @@ int main() {
     {
         const int sm2 = 16384 + 32768 + 1024;
         cudaFuncSetAttribute(kblock_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
+        for (int stt : {2, 16}) {
+            kblock_probe<<<148, 128, sm2>>>(32, 400, 1, 1, out, stt); cudaDeviceSynchronize();
+            printf("TS k-block body, 1 commit, with concurrent tcgen05.st traffic from 3 warps (wait every %2d): %7.1f clk per k-block  %s\n", stt, (double)out[1] / 400,
+                   cudaGetErrorString(cudaGetLastError()));
+        }
         for (int nc = 0; nc <= 2; ++nc)
             for (int fe = 0; fe <= 1; ++fe) {
                 kblock_probe<<<148, 128, sm2>>>(32, 400, nc, fe, out); cudaDeviceSynchronize();
