@@ -76,6 +76,7 @@ __global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, i
     // every load of this element is issued before the first dependent add: one L2 round trip instead of one per slab
     const float hp = a.h_prev ? a.h_prev[(long long)b * a.ld_hprev + j] : 0.f;
     const float m = a.mask ? a.mask[b] : 1.f;
+    const float cs_old = a.ctxsum ? a.ctxsum[(long long)b * a.ld_ctxsum + j] : 0.f;   // read with the other inputs, not at the tail
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     if (MODE == 0) {
         const float* x = a.xproj + row3;
@@ -120,7 +121,7 @@ __global__ void gru_gates_fwd_kernel(const __grid_constant__ GateFwdPack pack, i
     if (a.r) {
         a.r[idx] = r; a.u[idx] = u; a.c[idx] = c; a.p[idx] = pp;
     }
-    if (a.ctxsum) a.ctxsum[(long long)b * a.ld_ctxsum + j] += m * h;
+    if (a.ctxsum) a.ctxsum[(long long)b * a.ld_ctxsum + j] = cs_old + m * h;
 #ifdef NATS_TRACE_BUILD
     if (tr) printf("[trace gates_fwd] start %llu | wait_done +%llu | end +%llu ns\n", t0 % 100000000ull, t1 - t0, gtimer() - t0);
 #endif
