@@ -709,7 +709,7 @@ class DeviceArray(object):
 
 def _binop(name):
     def f(self, other):
-        return getattr(self.host(), name)(numpy.asarray(other))
+        return getattr(self.host(), name)(other.host() if isinstance(other, DeviceArray) else other)
     return f
 
 

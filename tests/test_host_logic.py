@@ -156,3 +156,27 @@ def test_toy_corpus_runs_through_the_data_path(tmp_path):
     x, xm, y, ym = N.prepare_data(sx, sy, maxlen=500, n_words=200)
     assert x.shape[1] == 4 and x.max() < 200 and xm.sum(0).min() >= 2 and y.shape[0] == ym.shape[0]
     assert sum(len(b[0]) for b in [(sx, sy)] + list(it)) == 200
+
+
+def test_device_array_behaves_like_the_host_array_f_next_used_to_return():
+    """DeviceArray (what f_next returns): NumPy sees an ordinary array, index lists select rows without leaving the
+    tensor's device, writes go to the host copy and are pushed back on the next .tensor() (here on a CPU tensor)."""
+    import torch
+    base = np.arange(12, dtype='float32').reshape(4, 3)
+    a = N.DeviceArray(torch.from_numpy(base.copy()))
+    assert a.shape == (4, 3) and a.ndim == 2 and len(a) == 4 and a.dtype == np.float32 and a.size == 12
+    np.testing.assert_array_equal(np.asarray(a), base)
+    np.testing.assert_array_equal(np.log(a + 1.0), np.log(base + 1.0))
+    np.testing.assert_array_equal(a[1], base[1])                      # scalar index -> host row
+    assert a[0, 2] == base[0, 2] and a[0].argmax() == 2
+    sel = a[[2, 0, 2]]                                                # index list -> stays a DeviceArray
+    assert isinstance(sel, N.DeviceArray)
+    np.testing.assert_array_equal(np.asarray(sel), base[[2, 0, 2]])
+    c = sel.copy()
+    c[:, 1] = -5.0                                                    # write: host copy, marked dirty
+    assert np.asarray(sel)[0, 1] == base[2, 1]                        # the source of the copy is untouched
+    np.testing.assert_array_equal(c.tensor().numpy()[:, 1], [-5.0, -5.0, -5.0])     # pushed back to the tensor
+    b = N.DeviceArray(torch.tensor([3, 1, 2], dtype=torch.int64))
+    assert b.dtype == np.int64 and int(b[0]) == 3
+    hyp = np.zeros(4, 'float32')
+    np.testing.assert_array_equal(hyp[:, None] - np.log(a + 1.0), -np.log(base + 1.0))
