@@ -171,8 +171,10 @@ def test_device_array_behaves_like_the_host_array_f_next_used_to_return():
     assert a[0, 2] == base[0, 2] and a[0].argmax() == 2
     sel = a[[2, 0, 2]]                                                # index list -> stays a DeviceArray
     assert isinstance(sel, N.DeviceArray)
+    c = sel.copy()                                                    # before any host access: a device-side clone
+    assert isinstance(c, N.DeviceArray)
     np.testing.assert_array_equal(np.asarray(sel), base[[2, 0, 2]])
-    c = sel.copy()
+    assert isinstance(sel.copy(), np.ndarray)                         # once on the host, copies are host arrays
     c[:, 1] = -5.0                                                    # write: host copy, marked dirty
     assert np.asarray(sel)[0, 1] == base[2, 1]                        # the source of the copy is untouched
     np.testing.assert_array_equal(c.tensor().numpy()[:, 1], [-5.0, -5.0, -5.0])     # pushed back to the tensor
