@@ -100,6 +100,7 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     enc_persistent_enable(getenv("NATS_PERSISTENT") ? atoi(getenv("NATS_PERSISTENT")) : 0);
     attention_set_cc_keep(getenv("NATS_CC_KEEP") ? atoi(getenv("NATS_CC_KEEP")) : 0);
     tma_gemm_set_ts(getenv("NATS_TS") ? atoi(getenv("NATS_TS")) : 1);
+    model_set_deferred_gates(getenv("NATS_DEFER_GATES") ? atoi(getenv("NATS_DEFER_GATES")) : 0);
     if (getenv("NATS_GEMM_DBG")) tma_gemm_debug_mode(atoi(getenv("NATS_GEMM_DBG")));
     if (getenv("NATS_TRACE_GATES")) gates_trace(atoi(getenv("NATS_TRACE_GATES")));
     if (getenv("NATS_TRACE")) { tma_gemm_trace(atoi(getenv("NATS_TRACE"))); }

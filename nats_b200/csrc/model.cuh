@@ -7,6 +7,8 @@
 
 namespace nats {
 
+void model_set_deferred_gates(int on);     // gates of step t at the head of the product kernel of step t+1 (opt-in, NATS_DEFER_GATES=1)
+
 struct EncBufs {
     float* emb_x;
     float* xproj[2];

@@ -3,6 +3,9 @@
 
 namespace nats {
 
+static int g_deferred_gates = 0;      // measured slower than the two-launch step: opt-in
+void model_set_deferred_gates(int on) { g_deferred_gates = on; }
+
 // ------------------------------------------------------------------------------------------------
 // encoder: embedding gather, input projections of both directions (one grouped GEMM), then Tx recurrent
 // steps where forward step s and backward step s run in the SAME launches (grouped GEMM + fused gate kernel).
@@ -49,6 +52,24 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
     }
     const bool fused = gru_step_eligible(n, D) && e.step_slab != nullptr;
     if (fused) NATS_CUDA_OK(memset_async(st, e.step_counters, 0, (size_t)e.step_counter_ints * sizeof(int)));
+    // Deferred gates: the gate arithmetic of step s runs at the head of the product kernel of step s+1 (GemmPre), so a
+    // recurrent step is ONE launch; only the last step's gates need their own kernel.
+    bool deferred = false;
+    unsigned* pre_counter = nullptr;
+    if (!fused && Tx > 1 && e.step_counters != nullptr && e.step_counter_ints >= 16) {
+        GemmProblem q[2];
+        q[0] = gemm_problem(e.cc, C, params + o.enc[0].Ucat, D3, e.part_a, D3, n, D3, D);
+        q[1] = gemm_problem(e.cc + D, C, params + o.enc[1].Ucat, D3, e.part_a + (long long)n * D3, D3, n, D3, D);
+        gemm_set_split(q[0], S, strideP);
+        gemm_set_split(q[1], S, strideP);
+        deferred = gemm_pre_supported(q, 2) && g_deferred_gates;
+        if (deferred) {
+            pre_counter = reinterpret_cast<unsigned*>(e.step_counters) + 8;
+            NATS_CUDA_OK(memset_async(st, pre_counter, 0, sizeof(unsigned)));
+        }
+    }
+    GemmPre pre;
+    memset(&pre, 0, sizeof(pre));
     for (int s = 0; s < Tx; ++s) {
         const int pf = s, pb = Tx - 1 - s;      // source positions handled by the forward / backward direction
         if (fused && s > 0) {                   // product + split-K fix-up + gates of both directions in ONE launch
@@ -79,6 +100,10 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
             gemm_set_split(q[0], S, strideP);
             gemm_set_split(q[1], S, strideP);
             q[0].b_static = q[1].b_static = 1;
+            if (deferred) {                     // `pre` holds the gates of step s-1 (filled at the end of the last iteration)
+                pre.kind = 1; pre.ngroups = 2; pre.B = n; pre.D = D; pre.counter = pre_counter; pre.ordinal = s;
+                q[0].pre = &pre;
+            }
             NATS_TRY(gemm_launch(st, q, 2, false, false, cfg));
         }
         GateFwd g[2];
@@ -101,6 +126,10 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
             }
             g[dir].ctxsum = e.ctxsum + dir * D;
             g[dir].ld_ctxsum = C;
+        }
+        if (deferred && s + 1 < Tx) {           // run by the next step's product kernel
+            pre.g[0] = g[0]; pre.g[1] = g[1];
+            continue;
         }
         NATS_TRY(gru_gates_fwd(st, g, 2, n, D, 0));
     }

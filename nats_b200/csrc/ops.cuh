@@ -31,6 +31,17 @@ struct GateFwd {
     float* ctxsum;          // optional running sum_t mask*h  (row stride ld_ctxsum), or NULL
     int ld_ctxsum;
 };
+// Work a product kernel runs BEFORE its main loop (tma_gemm.cu, TS kernel): the gates of the PREVIOUS recurrent step,
+// shared out over all CTAs of the launch and followed by a grid-wide barrier -- one kernel boundary per step instead
+// of two.  `counter` is a zero-initialised word that counts CTA arrivals monotonically over the launches of one
+// recurrence; `ordinal` is the 1-based index of this launch among them.
+struct GemmPre {
+    int kind;               // 0 none, 1 = GRU gate forward (mode 0)
+    int ngroups, B, D;
+    GateFwd g[2];
+    unsigned* counter;
+    int ordinal;
+};
 // mode 0: encoder GRU / decoder GRU_2 (candidate bias outside the reset gate);
 // mode 1: decoder GRU_1 (bias bx_1 inside the reset gate, context products in part2)
 int gru_gates_fwd(cudaStream_t st, const GateFwd* groups, int ngroups, int B, int D, int mode);

@@ -50,6 +50,21 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 // UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor), SWIZZLE_128B
+// non-suspending wait for the single latency-critical threads (MMA issuer): try_wait may park the thread for a
+// scheduler-defined interval when the phase is not complete yet; test_wait returns immediately
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {      // rows of 128 B (32 k), 8-row groups 1024 B apart
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
