@@ -518,7 +518,7 @@ int attention_bwd(const nats_ctx* ctx, cudaStream_t st, const AttBwd& a_in) {
     NATS_REQUIRE(a.A <= 32 * kMaxAk, "dim_att > 256 not supported by the attention backward kernel");
     {
         ProfScope ps(st, K_ATT_BWD_CTX);
-        NATS_CUDA_OK(launch_pdl(att_bwd_ctx_kernel, dim3(cdiv(a.B * a.C, 256)), dim3(256), 0, st, a));
+        NATS_CUDA_OK(launch_pdl(att_bwd_ctx_kernel, dim3(cdiv(a.B * a.C, 512)), dim3(512), 0, st, a));
     }
     const int nchunks = cdiv(a.Tx, kBwdRows);
     NATS_REQUIRE(a.dot_part != nullptr && a.soft_part != nullptr, "attention backward scratch");

@@ -38,6 +38,7 @@ __global__ void scatter_add_rows_kernel(float* __restrict__ dWemb, const int64_t
 struct GateFwdPack { GateFwd g[2]; int trace; };
 struct GateBwdPack { GateBwd g[2]; int trace; };
 
+constexpr int kGateThreads = 512;       // 125 CTAs per direction at D = 1000: measured 0.3 ms / step faster than 256-thread CTAs (grid completion)
 static int g_gate_trace = 0;
 static long long g_gate_no = 0;
 
@@ -234,10 +235,10 @@ int gru_gates_fwd(cudaStream_t st, const GateFwd* groups, int ngroups, int B, in
     memset(&pack, 0, sizeof(pack));
     for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
     if (g_gate_trace) { ++g_gate_no; pack.trace = (g_gate_no >= g_gate_trace - 1 && g_gate_no < g_gate_trace + 4) ? 1 : 0; }
-    dim3 grid(cdiv(B * D, 256), ngroups);
+    dim3 grid(cdiv(B * D, kGateThreads), ngroups);
     ProfScope ps(st, K_GATES_FWD);
-    if (mode == 0) NATS_CUDA_OK(launch_pdl(gru_gates_fwd_kernel<0>, grid, dim3(256), 0, st, pack, B, D));
-    else NATS_CUDA_OK(launch_pdl(gru_gates_fwd_kernel<1>, grid, dim3(256), 0, st, pack, B, D));
+    if (mode == 0) NATS_CUDA_OK(launch_pdl(gru_gates_fwd_kernel<0>, grid, dim3(kGateThreads), 0, st, pack, B, D));
+    else NATS_CUDA_OK(launch_pdl(gru_gates_fwd_kernel<1>, grid, dim3(kGateThreads), 0, st, pack, B, D));
     return 0;
 }
 int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, int D) {
@@ -245,9 +246,9 @@ int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, in
     GateBwdPack pack;
     memset(&pack, 0, sizeof(pack));
     for (int i = 0; i < ngroups; ++i) pack.g[i] = groups[i];
-    dim3 grid(cdiv(B * D, 256), ngroups);
+    dim3 grid(cdiv(B * D, kGateThreads), ngroups);
     ProfScope ps(st, K_GATES_BWD);
-    NATS_CUDA_OK(launch_pdl(gru_gates_bwd_kernel, grid, dim3(256), 0, st, pack, B, D));
+    NATS_CUDA_OK(launch_pdl(gru_gates_bwd_kernel, grid, dim3(kGateThreads), 0, st, pack, B, D));
     return 0;
 }
 
