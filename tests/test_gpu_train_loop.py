@@ -79,3 +79,29 @@ def test_train_then_generate(tmp_path):
     vit = TextIterator(va[0], va[1], dic, n_words=32, batch_size=4)
     v = N.pred_probs(graph.f_log_probs, N.prepare_data, opts, vit, verbose=False).mean()
     np.testing.assert_allclose(v, err2, rtol=1e-5)
+
+
+def test_py3_drivers(tmp_path):
+    """nats_b200.train_nats.main(job_id, params) and nats_b200.gen.main(...) -- the python-3 twins of the reference's
+    train_nats.py / gen.py -- on the synthetic corpus: same parameter dictionary, same output format."""
+    from nats_b200 import gen, train_nats
+    tr, va, dic, worddict = _corpus(tmp_path)
+    model = str(tmp_path / 'm.npz')
+    base = lambda p: os.path.basename(p)
+    params = {'data-dir': [str(tmp_path)], 'model': [model], 'train': [base(tr[0]), base(tr[1])],
+              'valid': [base(va[0]), base(va[1])], 'dictionary': [base(dic)], 'dim_word': [8], 'dim': [16],
+              'dim_att': [6], 'n-words': [32], 'patience': [1], 'optimizer': ['adadelta'], 'decay-c': [0.],
+              'clip-c': [100.], 'use-dropout': [False], 'learning-rate': [0.0001], 'reload': [False],
+              'batch-size': [4], 'finish-after': [11]}
+    err = train_nats.main(0, params)
+    assert np.isfinite(err) and os.path.exists(model) and os.path.exists(model + '.pkl')
+    out = str(tmp_path / 'gen.txt')
+    gen.main(model, dic, va[0], out, k=3, normalize=True, n_process=1, kl_factor=0.5, ctx_factor=0.5, state_factor=0.5)
+    lines = open(out).read().split('\n')
+    assert len([l for l in lines if l is not None]) >= 8
+    n_src = [len(l.split()) + 1 for l in open(va[0])]
+    for l, ns in zip(lines[:8], n_src):
+        toks = l.split()
+        assert len(toks) % 2 == 0
+        for w, p in zip(toks[0::2], toks[1::2]):
+            assert (w in worddict or w == 'UNK') and p.startswith('[') and 0 <= int(p[1:-1]) < ns
