@@ -10,6 +10,12 @@
 //   warps 0-7     : residual pass        (wait tma_full[s]; raw -> lo, 16-byte vectors; fence.proxy.async; arrive mma_full[s])
 //   warp 9 lane 0 : tcgen05.mma issuer   (wait mma_full[s]; 4 k-steps x 3 UMMA 128 x BN x 8; tcgen05.commit -> empty[s])
 //   warps 8-11    : epilogue             (tcgen05.ld of the four accumulators, fp32 sum, bias/accumulate/slab store)
+// Two kernels share the host side (tensor-map cache, grouping, split-K, PDL launch):
+//   tma_gemm_kernel     both operands from shared memory (above); used for the 128-wide tiles;
+//   tma_gemm_ts_kernel  skinny products (the batch, <= 64, on the N side): the 128-row weight operand goes through
+//                       TENSOR MEMORY (split warps tcgen05.st hi and lo; TS-form MMA) and the two products sharing A_hi
+//                       are stacked along N -- 2 MMAs per k-step, 56 KB instead of 120 KB of shared-memory traffic per
+//                       16 KB weight tile; optional pre-op (GemmPre, experimental).  Default for BN <= 64 (NATS_TS=0: off).
 // Requirements: 16-byte aligned base pointers and leading dimensions that are multiples of 4 floats (TMA strides);
 // anything else is served by the software-loader kernel in tc_gemm.cu.
 #include <cuda.h>
