@@ -1025,9 +1025,10 @@ def train(dim_word=100, dim=1000, dim_att=100, encoder='gru', decoder='gru_cond'
           finish_after=10000000, dispFreq=100, decay_c=0., clip_c=-1., lrate=0.01, n_words=100000, maxlen=100,
           optimizer='adadelta', batch_size=16, valid_batch_size=16, saveto='model.npz', validFreq=1000,
           saveFreq=1000, sampleFreq=100, datasets=[], valid_datasets=[], dictionary='', use_dropout=False,
-          reload_=False, verbose=False):
+          reload_=False, verbose=False, bucket_batches=0):
     """Same keyword surface, side effects (npz + options pickle, log lines) and return value as the reference's
-    train() (nats.py:1230-1539)."""
+    train() (nats.py:1230-1539).  `bucket_batches` (ours, default 0 = file order as the reference) lets the training
+    iterator sort that many batches by source length before cutting them (data_iterator.TextIterator)."""
     logging.basicConfig(level=logging.DEBUG, format="%(asctime)s: %(name)s: %(levelname)s: %(message)s")
     model_options = locals().copy()
 
@@ -1040,7 +1041,8 @@ def train(dim_word=100, dim=1000, dim_att=100, encoder='gru', decoder='gru_cond'
     logger.debug(pprint.pformat(model_options))
 
     print('Loading data')
-    train_it = TextIterator(datasets[0], datasets[1], dictionary, n_words=n_words, batch_size=batch_size)
+    train_it = TextIterator(datasets[0], datasets[1], dictionary, n_words=n_words, batch_size=batch_size,
+                            bucket_batches=bucket_batches)
     valid_it = TextIterator(valid_datasets[0], valid_datasets[1], dictionary, n_words=n_words,
                             batch_size=valid_batch_size)
 

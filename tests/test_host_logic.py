@@ -182,3 +182,36 @@ def test_device_array_behaves_like_the_host_array_f_next_used_to_return():
     assert b.dtype == np.int64 and int(b[0]) == 3
     hyp = np.zeros(4, 'float32')
     np.testing.assert_array_equal(hyp[:, None] - np.log(a + 1.0), -np.log(base + 1.0))
+
+
+def test_text_iterator_bucketing_keeps_the_epoch_and_cuts_padding(tmp_path):
+    """bucket_batches (ours, default off): every pair is still seen exactly once per epoch, the iterator rewinds like
+    the reference's, and the padded source area shrinks."""
+    from collections import OrderedDict
+    rng = np.random.RandomState(0)
+    words = ['w%d' % i for i in range(12)]
+    wd = OrderedDict([('eos', 0), ('UNK', 1)] + [(w, i + 2) for i, w in enumerate(words)])
+    with open(tmp_path / 'd.pkl', 'wb') as f:
+        pickle.dump(wd, f, protocol=2)
+    lens = rng.randint(2, 40, size=37)
+    with open(tmp_path / 's.txt', 'w') as fs, open(tmp_path / 't.txt', 'w') as ft:
+        for i, n in enumerate(lens):
+            fs.write(' '.join(rng.choice(words, size=n)) + '\n')
+            ft.write(' '.join(rng.choice(words, size=1 + i % 5)) + '\n')
+
+    def epoch(it):
+        batches = list(it)
+        pairs = sorted((tuple(s), tuple(t)) for sx, sy in batches for s, t in zip(sx, sy))
+        area = sum(max(len(s) for s in sx) * len(sx) for sx, _ in batches)
+        return batches, pairs, area
+
+    plain = TextIterator(str(tmp_path / 's.txt'), str(tmp_path / 't.txt'), str(tmp_path / 'd.pkl'), batch_size=4)
+    buck = TextIterator(str(tmp_path / 's.txt'), str(tmp_path / 't.txt'), str(tmp_path / 'd.pkl'), batch_size=4,
+                        bucket_batches=5)
+    b0, p0, a0 = epoch(plain)
+    b1, p1, a1 = epoch(buck)
+    assert p0 == p1 and len(p1) == 37                       # same multiset of pairs
+    assert sum(len(sx) for sx, _ in b1) == 37 and max(len(sx) for sx, _ in b1) <= 4
+    assert a1 < 0.8 * a0                                    # much less padding
+    _, p2, _ = epoch(buck)                                  # automatic rewind: a second epoch yields the same pairs
+    assert p2 == p1
