@@ -31,7 +31,7 @@ const char* kNames[K_COUNT] = {
     "gemm_mid_tt", "gemm_smallm_nn", "gemm_smallm_nt", "gemm_smallm_tn", "gemm_smallm_tt", "gru_gates_fwd",
     "gru_gates_bwd", "att_scores", "att_context", "att_bwd_ctx", "att_bwd_dalpha", "att_bwd_softmax", "nll_rows",
     "dlogits", "softmax_sample", "colsum", "reduce_splits", "embedding", "elementwise", "optimizer", "beam",
-    "memset", "tc_gemm_3xtf32", "tc_gemm_3xtf32_skinny", "gru_step_fwd_fused", "gru_step_bwd_fused", "enc_persistent_fwd", "enc_persistent_bwd"};
+    "memset", "tc_gemm_3xtf32", "tc_gemm_3xtf32_skinny", "enc_tc_fwd", "enc_tc_bwd"};
 }  // namespace
 const char* kclass_name(int cls) { return (cls >= 0 && cls < K_COUNT) ? kNames[cls] : "?"; }
 bool prof_enabled() { return g_prof.on; }
@@ -95,17 +95,14 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     int r = attention_setup(c);
     if (r == 0) r = tc_gemm_setup();
     if (r == 0) r = tma_gemm_setup();
-    if (r == 0) r = gru_step_setup();
-    if (r == 0) r = enc_persistent_setup(c);
-    enc_persistent_enable(getenv("NATS_PERSISTENT") ? atoi(getenv("NATS_PERSISTENT")) : 0);
+    if (r == 0) r = enc_tc_setup(c);
+    enc_tc_enable(getenv("NATS_ENC_TC") ? atoi(getenv("NATS_ENC_TC")) : 1);      // 0: per-step encoder path, 2 / 3: forward / backward only
     attention_set_cc_keep(getenv("NATS_CC_KEEP") ? atoi(getenv("NATS_CC_KEEP")) : 0);
     tma_gemm_set_ts(getenv("NATS_TS") ? atoi(getenv("NATS_TS")) : 1);
-    model_set_deferred_gates(getenv("NATS_DEFER_GATES") ? atoi(getenv("NATS_DEFER_GATES")) : 0);
     if (getenv("NATS_GEMM_DBG")) tma_gemm_debug_mode(atoi(getenv("NATS_GEMM_DBG")));
     if (getenv("NATS_TRACE_GATES")) gates_trace(atoi(getenv("NATS_TRACE_GATES")));
     if (getenv("NATS_TRACE")) { tma_gemm_trace(atoi(getenv("NATS_TRACE"))); }
     pdl_set(getenv("NATS_PDL") ? atoi(getenv("NATS_PDL")) : 1);
-    gru_step_enable(getenv("NATS_FUSED_STEP") ? atoi(getenv("NATS_FUSED_STEP")) : 0);
     gemm_set_tensor_cores(getenv("NATS_TC") ? atoi(getenv("NATS_TC")) : 2);
     if (r != 0) { cudaFree(c->dev_scratch); delete c; return r; }
     *out = c;
@@ -322,7 +319,6 @@ const float* nats_train_ws_view(const nats_dims_t* dims, int Tx, int Ty, int B, 
     if (!strcmp(name, "dec_alpha")) return w.d_alpha;
     if (!strcmp(name, "pctx")) return w.pctx;
     if (!strcmp(name, "logits")) return w.logits;
-    if (!strcmp(name, "step_counters")) return reinterpret_cast<const float*>(w.step_counters);
     return nullptr;
 }
 
@@ -347,7 +343,8 @@ int nats_sampler_init(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, co
     e.cc = ctx_out; e.ctxsum = w.ctxsum; e.xlen = w.xlen; e.xinv = w.xinv; e.ctx_mean = w.ctx_mean;
     e.init_state = init_state; e.part_a = w.part_a;
     e.gemm_scratch = w.gemm_scratch; e.gemm_scratch_floats = w.gemm_scratch_floats;
-    e.step_slab = w.step_slab; e.step_counters = w.step_counters; e.step_counter_ints = w.step_counter_ints;
+    e.enc_scratch = w.enc_scratch; e.enc_scratch_floats = w.enc_scratch_floats;
+    e.enc_counters = w.enc_counters; e.enc_counter_ints = w.enc_counter_ints;
     NATS_TRY(encoder_forward(ctx, st, *dims, params, x, nullptr, Tx, n, e));      // no masks (nats.py:801-804, 810)
     if (pctx_out) {
         const ParamOff o = param_offsets(*dims);
@@ -410,10 +407,6 @@ int nats_sampler_next(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, co
     s.alpha_out = alphaT; s.acc_alpha_out = acc_alpha_out; s.craw_out = w.craw; s.ctx_out = ctxs;
     s.acc_ctx_out = acc_ctx_out; s.h2 = state_out;
     s.part_a = w.part_a; s.part_b = w.part_b; s.part_c = w.part_c; s.part_d = w.part_d;
-    if (gru_step_eligible(n, D)) {
-        NATS_CUDA_OK(memset_async(st, w.step_counters, 0, (size_t)w.step_counter_ints * sizeof(int)));
-        s.step_slab = w.step_slab; s.step_counters = w.step_counters;
-    }
     NATS_TRY(decoder_step_forward(ctx, st, *dims, params, s));
 
     // readout (nats.py:850-861)

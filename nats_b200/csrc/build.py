@@ -16,9 +16,9 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, 'libnats_b200.so')
 OBJ = os.path.join(HERE, 'build')
-SOURCES = ['gemm.cu', 'tc_gemm.cu', 'tma_gemm.cu', 'gru_step.cu', 'enc_persistent.cu', 'ops_elem.cu', 'ops_att.cu', 'ops_readout.cu', 'ops_optim.cu', 'ops_beam.cu',
+SOURCES = ['gemm.cu', 'tc_gemm.cu', 'tma_gemm.cu', 'enc_tc.cu', 'ops_elem.cu', 'ops_att.cu', 'ops_readout.cu', 'ops_optim.cu', 'ops_beam.cu',
            'model_fwd.cu', 'model_bwd.cu', 'api.cu']
-HEADERS = ['common.cuh', 'prof.cuh', 'tc_common.cuh', 'gemm.cuh', 'ops.cuh', 'workspace.cuh', 'model.cuh',
+HEADERS = ['common.cuh', 'prof.cuh', 'tc_common.cuh', 'gemm.cuh', 'gates.cuh', 'ops.cuh', 'workspace.cuh', 'model.cuh',
            os.path.join(ROOT, 'include', 'nats_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = os.environ.get('NATS_NVCC_EXTRA', '').split() + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -1,6 +1,5 @@
-// gates.cuh -- the GRU gate arithmetic of one (sample, unit) element (nats.py:336-356, 505-518, 551-565), shared by the
-// stand-alone gate kernels (ops_elem.cu) and the product kernel's pre-op (tma_gemm.cu: the gates of step t run at the
-// head of the product of step t+1, one kernel boundary per recurrent step instead of two).
+// gates.cuh -- the GRU gate arithmetic of one (sample, unit) element (nats.py:336-356, 505-518, 551-565) for the
+// stand-alone gate kernels (ops_elem.cu).
 #pragma once
 #include "ops.cuh"
 

@@ -275,9 +275,6 @@ static bool tc_eligible(const GemmProblem* probs, int count) {
     return true;
 }
 
-bool gemm_pre_supported(const GemmProblem* probs, int count) {
-    return tc_eligible(probs, count) && g_use_tc >= 2 && tma_gemm_pre_supported(probs, count);
-}
 
 int gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool transA, bool transB, int cfg) {
     NATS_REQUIRE(count >= 1 && count <= kGemmMaxGroup, "gemm group size");

@@ -12,7 +12,6 @@
 
 namespace nats {
 
-struct GemmPre;      // ops.cuh
 
 struct GemmProblem {
     const float* A;
@@ -28,7 +27,6 @@ struct GemmProblem {
     long long strideP;     // distance between split slabs of C
     int accumulate;        // C += result (only with splitk == 1)
     int a_static, b_static; // operand is constant within the step (a weight matrix): PDL kernels may prefetch it early
-    const GemmPre* pre;     // optional pre-op of the launch (first problem of a group only; see tma_gemm_pre_supported)
 };
 
 constexpr int kGemmMaxGroup = 4;
@@ -68,9 +66,6 @@ int tc_gemm_setup();
 // TMA-fed variant (tma_gemm.cu): needs 16-byte aligned operands with leading dimensions multiple of 4
 int tma_gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool transA, bool transB);
 bool tma_gemm_eligible(const GemmProblem* probs, int count);
-// can this group carry a GemmPre?  (TMA-addressable, skinny, tensor-memory kernel enabled)
-bool tma_gemm_pre_supported(const GemmProblem* probs, int count);
-bool gemm_pre_supported(const GemmProblem* probs, int count);      // ... and the dispatcher would pick that kernel
 int tma_gemm_setup();
 void gemm_set_tensor_cores(int on);     // 1 (default): GEMM-shaped work goes to tcgen05; 0: exact-fp32 FFMA kernels
 int gemm_get_tensor_cores();

@@ -7,8 +7,6 @@
 
 namespace nats {
 
-void model_set_deferred_gates(int on);     // gates of step t at the head of the product kernel of step t+1 (opt-in, NATS_DEFER_GATES=1)
-
 struct EncBufs {
     float* emb_x;
     float* xproj[2];
@@ -17,7 +15,8 @@ struct EncBufs {
     float* ctxsum; float* xlen; float* xinv; float* ctx_mean; float* init_state;
     float* part_a;
     float* gemm_scratch; long long gemm_scratch_floats;
-    float* step_slab; int* step_counters; long long step_counter_ints;
+    float* enc_scratch; long long enc_scratch_floats;      // persistent encoder kernel (enc_tc.cu): NULL = per-step path
+    unsigned* enc_counters; long long enc_counter_ints;
 };
 // bi-GRU encoder + masked mean + ff_state (nats.py:700-724 / 795-813)
 int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, const float* params,
@@ -37,7 +36,6 @@ struct DecStep {
     float* alpha_out; float* acc_alpha_out; float* craw_out; float* ctx_out; float* acc_ctx_out;
     float* r2; float* u2; float* c2; float* p2; float* h2;
     float* part_a; float* part_b; float* part_c; float* part_d;
-    float* step_slab; int* step_counters;      // fused recurrent-step scratch (counters already zero)
 };
 // one _step_slice (nats.py:498-572)
 int decoder_step_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, const float* params,

@@ -193,10 +193,9 @@ int train_encoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
     const int cfg = gemm_step_cfg(B);
     const int S = gemm_pick_split(ctx, B, D, D3, 2);
     const long long strideP = 2LL * B * D;
-    const bool fused = gru_step_eligible(B, D);
-    const bool persistent = enc_persistent_eligible(ctx, B, D, 1);
-    if (persistent) {
-        EncPersistBwdArgs pa;
+    const bool persistent = enc_tc_eligible(ctx, B, D, 1);
+    if (persistent) {      // the whole reverse recurrence of both directions in ONE persistent tcgen05 launch (enc_tc.cu)
+        EncTcBwdArgs pa;
         memset(&pa, 0, sizeof(pa));
         for (int dir = 0; dir < 2; ++dir) {
             pa.Ucat[dir] = params + o.enc[dir].Ucat;
@@ -204,11 +203,11 @@ int train_encoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
             pa.dG[dir] = w.dGe[dir]; pa.dGx[dir] = w.dGex[dir];
         }
         pa.dcc = w.dcc; pa.mean_grad = w.dmean; pa.coef = w.xinv; pa.mask = x_mask; pa.cc = w.cc;
-        pa.bar = reinterpret_cast<unsigned*>(w.step_counters);
+        pa.bar = w.enc_counters; pa.bar_ints = w.enc_counter_ints;
+        pa.scratch = w.enc_scratch; pa.scratch_floats = w.enc_scratch_floats;
         pa.Tx = Tx; pa.n = B; pa.D = D;
-        NATS_TRY(enc_persistent_bwd(ctx, st, pa));
+        NATS_TRY(enc_tc_bwd(ctx, st, pa));
     }
-    if (fused && !persistent) NATS_CUDA_OK(memset_async(st, w.step_counters, 0, (size_t)w.step_counter_ints * sizeof(int)));
     for (int s = Tx - 1; s >= 0 && !persistent; --s) {
         const int pf = s, pb = Tx - 1 - s;
         GateBwd g[2];
@@ -220,10 +219,8 @@ int train_encoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
             g[dir].dh_a = w.dcc + (long long)pos * B * C + dir * D; g[dir].ld_a = C;
             if (s < Tx - 1) {
                 g[dir].dh_b = w.dh_elem + (long long)dir * B * D; g[dir].ld_b = D;
-                if (!fused) {
-                    g[dir].part = w.part_a + (long long)dir * B * D; g[dir].nsplit = S;
-                    g[dir].part_stride = strideP; g[dir].part_ld = D;
-                }
+                g[dir].part = w.part_a + (long long)dir * B * D; g[dir].nsplit = S;
+                g[dir].part_stride = strideP; g[dir].part_ld = D;
             }
             g[dir].mean_grad = w.dmean + dir * D; g[dir].ld_mean = C; g[dir].coef = w.xinv;   // nats.py:717
             g[dir].r = w.enc_r[dir] + so; g[dir].u = w.enc_u[dir] + so; g[dir].c = w.enc_c[dir] + so;
@@ -234,20 +231,7 @@ int train_encoder_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
             g[dir].dGx = w.dGex[dir] + (long long)pos * B * D3;
             g[dir].dh_elem = w.dh_elem + (long long)dir * B * D;
         }
-        if (fused && s < Tx - 1) {             // d h_t product + fix-up + gate backward of both directions in ONE launch
-            GruStepBwd f[2];
-            memset(f, 0, sizeof(f));
-            for (int dir = 0; dir < 2; ++dir) {
-                const int next_pos = dir == 0 ? pf + 1 : pb - 1;      // position handled by step s+1
-                f[dir].Ucat = params + o.enc[dir].Ucat;
-                f[dir].dG_next = w.dGe[dir] + (long long)next_pos * B * D3;
-                f[dir].g = g[dir];
-            }
-            NATS_TRY(gru_step_bwd(ctx, st, f, 2, B, D, w.step_slab, w.step_counters));
-            continue;
-        }
         NATS_TRY(gru_gates_bwd(st, g, 2, B, D));
-        if (fused) continue;                    // the fused kernel of step s-1 performs the product itself
         if (s > 0) {
             GemmProblem q[2];
             for (int dir = 0; dir < 2; ++dir) {

@@ -3,12 +3,10 @@
 
 namespace nats {
 
-static int g_deferred_gates = 0;      // measured slower than the two-launch step: opt-in
-void model_set_deferred_gates(int on) { g_deferred_gates = on; }
-
 // ------------------------------------------------------------------------------------------------
 // encoder: embedding gather, input projections of both directions (one grouped GEMM), then Tx recurrent
-// steps where forward step s and backward step s run in the SAME launches (grouped GEMM + fused gate kernel).
+// recurrent steps: ONE persistent tcgen05 launch for both directions (enc_tc.cu) or, for shapes it does not take,
+// per-step launches where forward step s and backward step s share a grouped GEMM + a 2-group gate kernel.
 // States are written straight into the concatenated context [Tx, n, 2D] (nats.py:713 needs no copy), the
 // masked sum for ctx_mean (nats.py:717) is accumulated by the gate kernel.
 // ------------------------------------------------------------------------------------------------
@@ -30,108 +28,56 @@ int encoder_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d, 
     const int S = gemm_pick_split(ctx, n, D3, D, 2);
     const int cfg = gemm_step_cfg(n);
     const long long strideP = 2LL * n * D3;
-    if (enc_persistent_eligible(ctx, n, D, 0) && e.step_counters != nullptr) {
-        // the whole recurrence of both directions in ONE persistent weight-stationary launch (enc_persistent.cu)
-        EncPersistFwdArgs pa;
+    if (enc_tc_eligible(ctx, n, D, 0) && e.enc_scratch != nullptr) {
+        // the whole recurrence of both directions in ONE persistent weight-stationary tcgen05 launch (enc_tc.cu)
+        EncTcFwdArgs pa;
         memset(&pa, 0, sizeof(pa));
         for (int dir = 0; dir < 2; ++dir) {
             pa.Ucat[dir] = params + o.enc[dir].Ucat; pa.xproj[dir] = e.xproj[dir];
             pa.r[dir] = e.r[dir]; pa.u[dir] = e.u[dir]; pa.c[dir] = e.c[dir]; pa.p[dir] = e.p[dir];
         }
         pa.mask = x_mask; pa.cc = e.cc; pa.ctxsum = e.ctxsum;
-        pa.bar = reinterpret_cast<unsigned*>(e.step_counters);
+        pa.bar = e.enc_counters; pa.bar_ints = e.enc_counter_ints;
+        pa.scratch = e.enc_scratch; pa.scratch_floats = e.enc_scratch_floats;
         pa.Tx = Tx; pa.n = n; pa.D = D;
-        NATS_TRY(enc_persistent_fwd(ctx, st, pa));
-        NATS_TRY(mask_lengths(st, x_mask, Tx, n, e.xlen, e.xinv));
-        NATS_TRY(scale_rows(st, e.ctxsum, e.xinv, n, C, e.ctx_mean));
-        GemmProblem pi0 = gemm_problem(e.ctx_mean, C, params + o.ff_state_W, D, e.init_state, D, n, D, C);
-        pi0.bias = params + o.ff_state_b;
-        NATS_TRY(gemm_auto(ctx, st, pi0, false, false, e.gemm_scratch, e.gemm_scratch_floats));
-        NATS_TRY(tanh_inplace(st, e.init_state, (long long)n * D));
-        return 0;
-    }
-    const bool fused = gru_step_eligible(n, D) && e.step_slab != nullptr;
-    if (fused) NATS_CUDA_OK(memset_async(st, e.step_counters, 0, (size_t)e.step_counter_ints * sizeof(int)));
-    // Deferred gates: the gate arithmetic of step s runs at the head of the product kernel of step s+1 (GemmPre), so a
-    // recurrent step is ONE launch; only the last step's gates need their own kernel.
-    bool deferred = false;
-    unsigned* pre_counter = nullptr;
-    if (!fused && Tx > 1 && e.step_counters != nullptr && e.step_counter_ints >= 16) {
-        GemmProblem q[2];
-        q[0] = gemm_problem(e.cc, C, params + o.enc[0].Ucat, D3, e.part_a, D3, n, D3, D);
-        q[1] = gemm_problem(e.cc + D, C, params + o.enc[1].Ucat, D3, e.part_a + (long long)n * D3, D3, n, D3, D);
-        gemm_set_split(q[0], S, strideP);
-        gemm_set_split(q[1], S, strideP);
-        deferred = gemm_pre_supported(q, 2) && g_deferred_gates;
-        if (deferred) {
-            pre_counter = reinterpret_cast<unsigned*>(e.step_counters) + 8;
-            NATS_CUDA_OK(memset_async(st, pre_counter, 0, sizeof(unsigned)));
-        }
-    }
-    GemmPre pre;
-    memset(&pre, 0, sizeof(pre));
-    for (int s = 0; s < Tx; ++s) {
-        const int pf = s, pb = Tx - 1 - s;      // source positions handled by the forward / backward direction
-        if (fused && s > 0) {                   // product + split-K fix-up + gates of both directions in ONE launch
-            GruStepFwd f[2];
-            memset(f, 0, sizeof(f));
+        NATS_TRY(enc_tc_fwd(ctx, st, pa));
+    } else {
+        // per-step path (shapes the persistent kernel does not take): grouped product of both directions + gate kernel
+        for (int s = 0; s < Tx; ++s) {
+            const int pf = s, pb = Tx - 1 - s;      // source positions handled by the forward / backward direction
+            if (s > 0) {                                                                     // nats.py:337, 345
+                GemmProblem q[2];
+                q[0] = gemm_problem(e.cc + (long long)(pf - 1) * n * C, C, params + o.enc[0].Ucat, D3, e.part_a, D3, n, D3, D);
+                q[1] = gemm_problem(e.cc + (long long)(pb + 1) * n * C + D, C, params + o.enc[1].Ucat, D3,
+                                    e.part_a + (long long)n * D3, D3, n, D3, D);
+                gemm_set_split(q[0], S, strideP);
+                gemm_set_split(q[1], S, strideP);
+                q[0].b_static = q[1].b_static = 1;
+                NATS_TRY(gemm_launch(st, q, 2, false, false, cfg));
+            }
+            GateFwd g[2];
+            memset(g, 0, sizeof(g));
             for (int dir = 0; dir < 2; ++dir) {
                 const int pos = dir == 0 ? pf : pb;
                 const int prev = dir == 0 ? pf - 1 : pb + 1;
-                f[dir].Ucat = params + o.enc[dir].Ucat;
-                f[dir].xproj = e.xproj[dir] + (long long)pos * n * D3;
-                f[dir].h_prev = e.cc + (long long)prev * n * C + dir * D; f[dir].ld_hprev = C;
-                f[dir].mask = x_mask ? x_mask + (long long)pos * n : nullptr;
-                f[dir].h_out = e.cc + (long long)pos * n * C + dir * D; f[dir].ld_hout = C;
+                g[dir].part = e.part_a + (long long)dir * n * D3;
+                g[dir].nsplit = s > 0 ? S : 0;
+                g[dir].part_stride = strideP;
+                g[dir].xproj = e.xproj[dir] + (long long)pos * n * D3;
+                g[dir].h_prev = s > 0 ? e.cc + (long long)prev * n * C + dir * D : nullptr;
+                g[dir].ld_hprev = C;
+                g[dir].mask = x_mask ? x_mask + (long long)pos * n : nullptr;
+                g[dir].h_out = e.cc + (long long)pos * n * C + dir * D;
+                g[dir].ld_hout = C;
                 if (e.r[dir]) {
                     const long long so = (long long)pos * n * D;
-                    f[dir].r = e.r[dir] + so; f[dir].u = e.u[dir] + so; f[dir].c = e.c[dir] + so; f[dir].p = e.p[dir] + so;
+                    g[dir].r = e.r[dir] + so; g[dir].u = e.u[dir] + so; g[dir].c = e.c[dir] + so; g[dir].p = e.p[dir] + so;
                 }
-                f[dir].ctxsum = e.ctxsum + dir * D; f[dir].ld_ctxsum = C;
+                g[dir].ctxsum = e.ctxsum + dir * D;
+                g[dir].ld_ctxsum = C;
             }
-            NATS_TRY(gru_step_fwd(ctx, st, f, 2, n, D, e.step_slab, e.step_counters));
-            continue;
+            NATS_TRY(gru_gates_fwd(st, g, 2, n, D, 0));
         }
-        if (s > 0) {                                                                     // nats.py:337, 345
-            GemmProblem q[2];
-            q[0] = gemm_problem(e.cc + (long long)(pf - 1) * n * C, C, params + o.enc[0].Ucat, D3, e.part_a, D3, n, D3, D);
-            q[1] = gemm_problem(e.cc + (long long)(pb + 1) * n * C + D, C, params + o.enc[1].Ucat, D3,
-                                e.part_a + (long long)n * D3, D3, n, D3, D);
-            gemm_set_split(q[0], S, strideP);
-            gemm_set_split(q[1], S, strideP);
-            q[0].b_static = q[1].b_static = 1;
-            if (deferred) {                     // `pre` holds the gates of step s-1 (filled at the end of the last iteration)
-                pre.kind = 1; pre.ngroups = 2; pre.B = n; pre.D = D; pre.counter = pre_counter; pre.ordinal = s;
-                q[0].pre = &pre;
-            }
-            NATS_TRY(gemm_launch(st, q, 2, false, false, cfg));
-        }
-        GateFwd g[2];
-        memset(g, 0, sizeof(g));
-        for (int dir = 0; dir < 2; ++dir) {
-            const int pos = dir == 0 ? pf : pb;
-            const int prev = dir == 0 ? pf - 1 : pb + 1;
-            g[dir].part = e.part_a + (long long)dir * n * D3;
-            g[dir].nsplit = s > 0 ? S : 0;
-            g[dir].part_stride = strideP;
-            g[dir].xproj = e.xproj[dir] + (long long)pos * n * D3;
-            g[dir].h_prev = s > 0 ? e.cc + (long long)prev * n * C + dir * D : nullptr;
-            g[dir].ld_hprev = C;
-            g[dir].mask = x_mask ? x_mask + (long long)pos * n : nullptr;
-            g[dir].h_out = e.cc + (long long)pos * n * C + dir * D;
-            g[dir].ld_hout = C;
-            if (e.r[dir]) {
-                const long long so = (long long)pos * n * D;
-                g[dir].r = e.r[dir] + so; g[dir].u = e.u[dir] + so; g[dir].c = e.c[dir] + so; g[dir].p = e.p[dir] + so;
-            }
-            g[dir].ctxsum = e.ctxsum + dir * D;
-            g[dir].ld_ctxsum = C;
-        }
-        if (deferred && s + 1 < Tx) {           // run by the next step's product kernel
-            pre.g[0] = g[0]; pre.g[1] = g[1];
-            continue;
-        }
-        NATS_TRY(gru_gates_fwd(st, g, 2, n, D, 0));
     }
     NATS_TRY(mask_lengths(st, x_mask, Tx, n, e.xlen, e.xinv));
     NATS_TRY(scale_rows(st, e.ctxsum, e.xinv, n, C, e.ctx_mean));                        // nats.py:717 / 810
@@ -155,15 +101,7 @@ int decoder_step_forward(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t
     const int S1 = gemm_pick_split(ctx, n, D3, D);
     const int S2 = gemm_pick_split(ctx, n, D3, C);
     const long long sp3 = (long long)n * D3;
-    if (gru_step_eligible(n, D) && s.step_slab != nullptr) {      // GRU_2 in one fused launch (nats.py:505-518)
-        GruStepFwd f;
-        memset(&f, 0, sizeof(f));
-        f.Ucat = params + o.dec.Ucat; f.xproj = s.xproj;
-        f.h_prev = s.h_prev; f.ld_hprev = D; f.mask = s.ymask;
-        f.h_out = s.h1; f.ld_hout = D;
-        f.r = s.r1; f.u = s.u1; f.c = s.c1; f.p = s.p1;
-        NATS_TRY(gru_step_fwd(ctx, st, &f, 1, n, D, s.step_slab, s.step_counters));
-    } else {   // GRU_2 recurrent product (nats.py:505, 512)
+    {   // GRU_2 recurrent product (nats.py:505, 512)
         GemmProblem q = gemm_problem(s.h_prev, D, params + o.dec.Ucat, D3, s.part_b, D3, n, D3, D);
         gemm_set_split(q, S1, sp3);
         q.b_static = 1;
@@ -238,7 +176,8 @@ int train_encoder_fwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
     e.cc = w.cc; e.ctxsum = w.ctxsum; e.xlen = w.xlen; e.xinv = w.xinv; e.ctx_mean = w.ctx_mean;
     e.init_state = w.init_state; e.part_a = w.part_a;
     e.gemm_scratch = w.gemm_scratch; e.gemm_scratch_floats = w.gemm_scratch_floats;
-    e.step_slab = w.step_slab; e.step_counters = w.step_counters; e.step_counter_ints = w.step_counter_ints;
+    e.enc_scratch = w.enc_scratch; e.enc_scratch_floats = w.enc_scratch_floats;
+    e.enc_counters = w.enc_counters; e.enc_counter_ints = w.enc_counter_ints;
     return encoder_forward(ctx, st, d, params, x, x_mask, Tx, B, e);
 }
 
@@ -260,7 +199,6 @@ int train_decoder_fwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
         p.bias = params + o.b_att;
         NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
     }
-    NATS_CUDA_OK(memset_async(st, w.step_counters, 0, (size_t)w.step_counter_ints * sizeof(int)));
     NATS_CUDA_OK(memset_async(st, w.d_accalpha, 0, (size_t)B * Tx * sizeof(float)));   // nats.py:599-603
     NATS_CUDA_OK(memset_async(st, w.d_accctx, 0, (size_t)B * C * sizeof(float)));
     for (int t = 0; t < Ty; ++t) {
@@ -283,7 +221,6 @@ int train_decoder_fwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
         s.craw_out = w.d_craw + rC; s.ctx_out = w.d_ctx + rC;
         s.r2 = w.d_r2 + rD; s.u2 = w.d_u2 + rD; s.c2 = w.d_c2 + rD; s.p2 = w.d_p2 + rD; s.h2 = w.d_h2 + rD;
         s.part_a = w.part_a; s.part_b = w.part_b; s.part_c = w.part_c; s.part_d = w.part_d;
-        s.step_slab = w.step_slab; s.step_counters = w.step_counters;
         NATS_TRY(decoder_step_forward(ctx, st, d, params, s));
     }
     return 0;

@@ -31,17 +31,6 @@ struct GateFwd {
     float* ctxsum;          // optional running sum_t mask*h  (row stride ld_ctxsum), or NULL
     int ld_ctxsum;
 };
-// Work a product kernel runs BEFORE its main loop (tma_gemm.cu, TS kernel): the gates of the PREVIOUS recurrent step,
-// shared out over all CTAs of the launch and followed by a grid-wide barrier -- one kernel boundary per step instead
-// of two.  `counter` is a zero-initialised word that counts CTA arrivals monotonically over the launches of one
-// recurrence; `ordinal` is the 1-based index of this launch among them.
-struct GemmPre {
-    int kind;               // 0 none, 1 = GRU gate forward (mode 0)
-    int ngroups, B, D;
-    GateFwd g[2];
-    unsigned* counter;
-    int ordinal;
-};
 // mode 0: encoder GRU / decoder GRU_2 (candidate bias outside the reset gate);
 // mode 1: decoder GRU_1 (bias bx_1 inside the reset gate, context products in part2)
 int gru_gates_fwd(cudaStream_t st, const GateFwd* groups, int ngroups, int B, int D, int mode);
@@ -62,54 +51,37 @@ struct GateBwd {
 };
 int gru_gates_bwd(cudaStream_t st, const GateBwd* groups, int ngroups, int B, int D);
 
-// ------------------------------------------------------------------ fused recurrent step (gru_step.cu)
-// One launch = tcgen05 product with the packed recurrent weights + split-K fix-up + the gate arithmetic above.
-struct GruStepFwd {
-    const float* Ucat;          // [D, 3D] = [U | Ux]
-    const float* xproj;         // [B,3D] input projection incl. biases
-    const float* h_prev; int ld_hprev;
-    const float* mask;          // [B] or NULL
-    float* h_out; int ld_hout;
-    float* r; float* u; float* c; float* p;     // save slots or NULL
-    float* ctxsum; int ld_ctxsum;               // or NULL
-};
-struct GruStepBwd {
-    const float* Ucat;
-    const float* dG_next;       // [B,3D]: gate derivatives of the step processed just before (time t+1)
-    GateBwd g;                  // arguments of THIS step's gate backward (part / part2 fields unused)
-};
-bool gru_step_eligible(int B, int D);
-void gru_step_enable(int on);
-long long gru_step_slab_floats(int B, int D);
-long long gru_step_counter_ints(int D);
-int gru_step_setup();
-int gru_step_fwd(const nats_ctx* ctx, cudaStream_t st, const GruStepFwd* dirs, int ndir, int B, int D, float* slab,
-                 int* counters);
-int gru_step_bwd(const nats_ctx* ctx, cudaStream_t st, const GruStepBwd* dirs, int ndir, int B, int D, float* slab,
-                 int* counters);
-
-// ------------------------------------------------------------------ persistent encoder recurrence (enc_persistent.cu)
-struct EncPersistFwdArgs {
+// ------------------------------------------------------------------ persistent tcgen05 encoder recurrence (enc_tc.cu)
+struct EncTcFwdArgs {
     const float* Ucat[2]; const float* xproj[2]; const float* mask; float* cc;
     float* r[2]; float* u[2]; float* c[2]; float* p[2];      // NULL = do not save
-    float* ctxsum; unsigned* bar; int Tx, n, D;
+    float* ctxsum;
+    unsigned* bar; long long bar_ints;                        // counters (zeroed by the call)
+    float* scratch; long long scratch_floats;                 // residual side buffer + K-partial slabs
+    unsigned long long* dbg;                                  // optional phase stamps (NULL = off)
+    int Tx, n, D;
 };
-struct EncPersistBwdArgs {
+struct EncTcBwdArgs {
     const float* Ucat[2]; const float* dcc; const float* mean_grad; const float* coef; const float* mask; const float* cc;
     const float* r[2]; const float* u[2]; const float* c[2]; const float* p[2];
-    float* dG[2]; float* dGx[2]; unsigned* bar; int Tx, n, D;
+    float* dG[2]; float* dGx[2];
+    unsigned* bar; long long bar_ints; float* scratch; long long scratch_floats;
+    unsigned long long* dbg;
+    int Tx, n, D;
 };
+bool enc_tc_eligible(const nats_ctx* ctx, int n, int D, int pass);   // pass: 0 forward, 1 backward
+void enc_tc_enable(int on);                                          // 0 off, 1 both passes (default), 2 forward only, 3 backward only
+int enc_tc_setup(const nats_ctx* ctx);
+long long enc_tc_scratch_floats(int n, int D);     // upper bounds, independent of the device
+long long enc_tc_counter_ints();
+int enc_tc_fwd(const nats_ctx* ctx, cudaStream_t st, const EncTcFwdArgs& a);
+int enc_tc_bwd(const nats_ctx* ctx, cudaStream_t st, const EncTcBwdArgs& a);
 void gates_trace(int on);
 void attention_set_cc_keep(int mode);
 void tma_gemm_trace(int on);
 void tma_gemm_debug_mode(int mode);
 void tma_gemm_set_ts(int on);
 int tma_gemm_get_ts();
-bool enc_persistent_eligible(const nats_ctx* ctx, int n, int D, int pass);   // pass: 0 forward, 1 backward
-void enc_persistent_enable(int on);
-int enc_persistent_setup(const nats_ctx* ctx);
-int enc_persistent_fwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistFwdArgs& a);
-int enc_persistent_bwd(const nats_ctx* ctx, cudaStream_t st, const EncPersistBwdArgs& a);
 
 // ------------------------------------------------------------------ small elementwise / reductions
 int tanh_inplace(cudaStream_t st, float* x, long long n);

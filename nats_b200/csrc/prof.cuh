@@ -26,9 +26,7 @@ enum KClass {
     K_MEMSET,
     K_TC_GEMM,           // tcgen05 3xTF32, 128 x 128 tiles
     K_TC_GEMM_SKINNY,    // tcgen05 3xTF32, swapped roles (batch on the N side)
-    K_GRU_STEP_FWD,      // fused recurrent step: tcgen05 GEMM + split-K fix-up + gates
-    K_GRU_STEP_BWD,
-    K_ENC_PERSIST_FWD,   // persistent weight-stationary bidirectional encoder recurrence (one launch per pass)
+    K_ENC_PERSIST_FWD,   // persistent weight-stationary tcgen05 bidirectional encoder recurrence (one launch per pass)
     K_ENC_PERSIST_BWD,
     K_COUNT
 };

@@ -1,4 +1,4 @@
-// tc_common.cuh -- device helpers shared by the tcgen05 / TMA kernels (tma_gemm.cu, gru_step.cu).
+// tc_common.cuh -- device helpers shared by the tcgen05 / TMA kernels (tma_gemm.cu, enc_tc.cu).
 #pragma once
 #include <cuda.h>
 

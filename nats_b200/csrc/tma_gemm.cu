@@ -15,7 +15,7 @@
 //   tma_gemm_ts_kernel  skinny products (the batch, <= 64, on the N side): the 128-row weight operand goes through
 //                       TENSOR MEMORY (split warps tcgen05.st hi and lo; TS-form MMA) and the two products sharing A_hi
 //                       are stacked along N -- 2 MMAs per k-step, 56 KB instead of 120 KB of shared-memory traffic per
-//                       16 KB weight tile; optional pre-op (GemmPre, experimental).  Default for BN <= 64 (NATS_TS=0: off).
+//                       16 KB weight tile.  Default for BN <= 64 (NATS_TS=0: off).
 // Requirements: 16-byte aligned base pointers and leading dimensions that are multiples of 4 floats (TMA strides);
 // anything else is served by the software-loader kernel in tc_gemm.cu.
 #include <cuda.h>
@@ -25,7 +25,6 @@
 
 #include "gemm.cuh"
 #include "tc_common.cuh"
-#include "gates.cuh"
 
 namespace nats {
 
@@ -56,8 +55,6 @@ struct alignas(64) TmaGroup {
     int zstart[kMaxGroup + 1];
     int count;
     int trace;           // debug: CTA (0,0,0) prints its phase timestamps (NATS_TRACE)
-    GemmPre pre;         // optional pre-op (TS kernel only)
-    unsigned pre_target; // arrivals the grid barrier after the pre-op waits for
     int dbg_mode;        // debug timing experiments (WRONG results): 1 = skip the residual arithmetic, 2 = hi*hi product only
 };
 
@@ -352,40 +349,6 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
 // split warps read the raw tile ONCE and write both halves  hi = trunc_tf32(x),  lo = x - hi  into TMEM with
 // tcgen05.st (lane = row m, column = k), and the three MMAs of a k-step read A from TMEM: 56 KB per tile.
 //   raw stage (shared, NR deep): [A_raw 16 KB | B_raw | B_lo]      A stage (TMEM, NL deep): [hi 32 cols | lo 32 cols]
-// The pre-op of a launch: every CTA takes an equal share of the (direction, sample, unit) elements of the previous
-// step's gates, then all CTAs meet at a monotonic arrive/spin barrier (the grid is co-resident: one CTA per SM by its
-// shared-memory footprint, and a dependent grid is only launched once every CTA of its primary has started).
-__device__ __forceinline__ void run_pre_op(const TmaGroup& grp) {
-    pdl_wait();                                       // the previous product's slabs and the previous gates are complete
-    const GemmPre& pre = grp.pre;
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int ncta = gridDim.x * gridDim.y * gridDim.z;
-    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    const int per_dir = pre.B * pre.D, total = pre.ngroups * per_dir;
-    const int per = (total + ncta - 1) / ncta;
-    const int beg = cta * per, end = min(total, beg + per);
-    for (int e = beg + tid; e < end; e += nth) {
-        const int dir = e / per_dir, idx = e - dir * per_dir;
-        const int b = idx / pre.D, j = idx - b * pre.D;
-        if (dir == 0) gru_gate_fwd_elem<0>(pre.g[0], b, j, pre.D, idx);
-        else gru_gate_fwd_elem<0>(pre.g[1], b, j, pre.D, idx);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        atomicAdd(pre.counter, 1u);
-        const long long t0 = clock64();
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pre.counter) : "memory");
-            if (v >= grp.pre_target) break;
-            if (clock64() - t0 > 4000000000LL) __trap();        // ~2 s: never hang the device
-        } while (true);
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 template <int BN, int NR, int NL, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_constant__ TmaGroup grp) {
     constexpr uint32_t kABytes = 128 * 128, kBBytes = BN * 128;
@@ -424,10 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
     z -= grp.zstart[g];
     const int split = z % P.splitk, batch = z / P.splitk;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
-    if (m0 >= P.Ma || n0 >= P.Nb) {                   // idle CTA of a ragged group: still owes its share of the pre-op
-        if (grp.pre.kind) run_pre_op(grp);
-        return;
-    }
+    if (m0 >= P.Ma || n0 >= P.Nb) return;
 
     const int kbeg = split * P.kchunk;
     const int kend = min(P.K, kbeg + P.kchunk);
@@ -456,7 +416,6 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
     const uint32_t tmem_a0 = tmem_d + kAccCols;
     if (tr && tid == 0) tr_s[1] = gtimer();
     pdl_trigger();
-    const bool has_pre = grp.pre.kind != 0;
     const int npre_w = P.a_static ? min(nkb, NR) : 0;      // weight tiles requested before any dependency wait
     if (warp == 8 && lane == 0) {
         for (int kb = 0; kb < npre_w; ++kb) {
@@ -471,7 +430,6 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
             }
         }
     }
-    if (has_pre) run_pre_op(grp);
 
     if (warp < 8) {
         // ===================== split pass: raw A tile -> (hi, lo) in tensor memory; raw B tile -> B_lo in shared =====
@@ -539,8 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
             // ===================== TMA producer (as in the SS kernel) =====================
             const int npre = npre_w;
             if (tr) tr_s[2] = gtimer();
-            if (!has_pre) pdl_wait();
-            else asm volatile("fence.proxy.async;" ::: "memory");      // the h tiles were written by generic stores of other CTAs
+            pdl_wait();
             if (tr) tr_s[3] = gtimer();
             for (int kb = 0; kb < nkb; ++kb) {
                 const int sr = kb % NR;
@@ -806,14 +763,6 @@ int tma_map_3d(const float* ptr, long long inner, long long outer, long long ld,
 }
 bool tma_available() { return g_encode != nullptr; }
 
-bool tma_gemm_pre_supported(const GemmProblem* probs, int count) {
-    if (!g_ts_mode || !tma_gemm_eligible(probs, count)) return false;
-    int maxM = 0, maxN = 0;
-    for (int i = 0; i < count; ++i) { maxM = max(maxM, probs[i].M); maxN = max(maxN, probs[i].N); }
-    const bool swapped = maxM < 128 && maxN > maxM;
-    return (swapped ? maxM : maxN) <= 64;
-}
-
 int tma_map_tile3d(const float* ptr, long long d0, long long d1, long long d2, long long stride1, long long stride2, int b0,
                    int b1, int b2, CUtensorMap* out) {
     NATS_REQUIRE(g_encode != nullptr, "tensor maps not available");
@@ -923,11 +872,6 @@ int tma_gemm_launch(cudaStream_t st, const GemmProblem* probs, int count, bool t
     for (int i = count; i < kMaxGroup; ++i) grp.zstart[i + 1] = z;
     if (ga == 0 || gb == 0 || z == 0) return 0;
     dim3 grid(ga, gb, z);
-    if (probs[0].pre != nullptr && probs[0].pre->kind != 0) {
-        NATS_REQUIRE(g_ts_mode && BN <= 64, "pre-op needs the tensor-memory product kernel");
-        grp.pre = *probs[0].pre;
-        grp.pre_target = (unsigned)grp.pre.ordinal * (unsigned)(ga * gb * z);
-    }
     if (BN == 32) return launch_bn<32, 8, 2>(st, grp, a_mn, b_mn, grid, flops, bytes);
     if (BN == 64) return launch_bn<64, 6, 2>(st, grp, a_mn, b_mn, grid, flops, bytes);
     return launch_bn<128, 5, 2>(st, grp, a_mn, b_mn, grid, flops, bytes);

@@ -145,9 +145,10 @@ struct TrainWS {
     float* gemm_scratch; // split-K slabs for gemm_auto
     int64_t gemm_scratch_floats;
     float* red_scratch;  // column-sum scratch: 64 * max(V, 3D, C) floats
-    float* step_slab;    // split-K exchange of the fused recurrent-step kernels
-    int* step_counters;  // their per-tile tickets (zeroed before every recurrence)
-    int64_t step_counter_ints;
+    float* enc_scratch;  // persistent encoder kernels (enc_tc.cu): residual side buffer + K-partial words
+    int64_t enc_scratch_floats;
+    unsigned* enc_counters;
+    int64_t enc_counter_ints;
     int64_t bytes;
 };
 
@@ -191,9 +192,10 @@ inline TrainWS carve_train(const nats_dims_t& d, int Tx, int Ty, int B, void* ba
     w.gemm_scratch_floats = 8LL << 20;
     w.gemm_scratch = c.f(w.gemm_scratch_floats);
     { int64_t mx = V; if (3 * D > mx) mx = 3 * D; w.red_scratch = c.f(64 * mx); }
-    w.step_slab = c.f(gru_step_slab_floats(B, (int)D));
-    w.step_counter_ints = gru_step_counter_ints((int)D);
-    w.step_counters = c.take<int>(w.step_counter_ints);
+    w.enc_scratch_floats = enc_tc_scratch_floats(B, (int)D);
+    w.enc_scratch = c.f(w.enc_scratch_floats);
+    w.enc_counter_ints = enc_tc_counter_ints();
+    w.enc_counters = c.take<unsigned>(w.enc_counter_ints);
     w.bytes = round_up64(c.off, 256);
     return w;
 }
@@ -220,9 +222,10 @@ struct SamplerWS {
     float* logits;      // [n, V]
     float* gemm_scratch;
     int64_t gemm_scratch_floats;
-    float* step_slab;
-    int* step_counters;
-    int64_t step_counter_ints;
+    float* enc_scratch;
+    int64_t enc_scratch_floats;
+    unsigned* enc_counters;
+    int64_t enc_counter_ints;
     int64_t bytes;
 };
 
@@ -243,9 +246,10 @@ inline SamplerWS carve_sampler(const nats_dims_t& d, int Tx, int n, void* base) 
     w.h1 = c.f(n * D); w.ps = c.f(n * A); w.craw = c.f(n * C); w.L = c.f(n * W); w.logits = c.f(n * V);
     w.gemm_scratch_floats = 4LL << 20;
     w.gemm_scratch = c.f(w.gemm_scratch_floats);
-    w.step_slab = c.f(gru_step_slab_floats(n, (int)D));
-    w.step_counter_ints = gru_step_counter_ints((int)D);
-    w.step_counters = c.take<int>(w.step_counter_ints);
+    w.enc_scratch_floats = enc_tc_scratch_floats(n, (int)D);
+    w.enc_scratch = c.f(w.enc_scratch_floats);
+    w.enc_counter_ints = enc_tc_counter_ints();
+    w.enc_counters = c.take<unsigned>(w.enc_counter_ints);
     w.bytes = round_up64(c.off, 256);
     return w;
 }
