@@ -64,7 +64,7 @@ struct EncTc {
     // ---- exchange
     float* lo;                  // [2 dir][2 parity][n][Kp]
     unsigned long long* slab;   // [2 dir][NT][S][NG][BN][dpc] K partials as {value, step tag} words (filled with 0xff before the launch)
-    unsigned* bar;              // [0], [32]: direction counters (zero-initialised)
+    unsigned* bar;              // [32 * (dir*NT + tile)]: arrivals of the tile's CTAs (zero-initialised)
     unsigned long long* dbg;    // optional phase stamps of CTA 0 (NULL = off)
     int Tx, n, D, Kp;
     int NT, S, dpc, dps, Kc, nkbA, NS;
@@ -83,15 +83,6 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
             : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (!ok && clock64() - t0 > kSpinLimit) __trap();
     } while (!ok);
-}
-__device__ __forceinline__ void flag_wait(const unsigned* ctr, unsigned target) {
-    const long long t0 = clock64();
-    unsigned v;
-    do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        if (v >= target) break;
-        if (clock64() - t0 > kSpinLimit) __trap();
-    } while (true);
 }
 __device__ __forceinline__ void flag_arrive(unsigned* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
@@ -149,7 +140,6 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
     const int klen = max(0, kend - kbeg);
     const int nkb = (klen + 31) >> 5;
     const int NS = a.NS;
-    const unsigned nact = (unsigned)(NT * S);                // CTAs of one direction
 
     const uint32_t sA = smem_u32(smem);
     if (sA & 1023u) __trap();                                // the UMMA / TMA swizzle atoms need 1024-byte alignment
@@ -223,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    unsigned* ctr = a.bar + dir * kCtrStride;
+    unsigned* tctr = a.bar + (dir * NT + tile) * kCtrStride;      // arrivals of this row tile's CTAs (S per step)
     const bool stamp = a.dbg != nullptr && blockIdx.x == 0;
 #define ENC_STAMP(i) do { a.dbg[i] = gtimer(); a.dbg[32 + (i)] = (unsigned long long)clock64(); } while (0)
 
@@ -235,13 +225,36 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
     const int npair = (nkb + 1) >> 1;
     if (warp == 4) {
         // ============================================================ flag poll + TMA producer
-        if (lane == 0) {
-            uint32_t dpar = 0;                               // parity bit per pair slot: next phase of done[slot] to wait for
-            for (int s = 1; s < Tx; ++s) {
+        // Dependencies are tracked per ROW TILE (S arrivals per step each): this CTA's operand columns [kbeg, kcov) are
+        // produced by a few tiles only (9-10 of 24 forward, all 8 backward), so it does not wait for the slowest CTA of
+        // the whole direction.  Lane l polls the counter of tile l; the warp proceeds when every needed tile is complete.
+        const int kcov = min(Ktot, kbeg + 32 * nkb);
+        bool need = false;
+        if (lane < NT) {
+            const int u0 = lane * dpc, u1 = min(D, u0 + dpc);          // units finished by tile `lane`
+            for (int g = 0; g < (BWD ? 3 : 1); ++g) need = need || (g * D + u0 < kcov && g * D + u1 > kbeg);
+        }
+        const unsigned* pctr = a.bar + (dir * NT + lane) * kCtrStride;
+        uint32_t dpar = 0;                                   // parity bit per pair slot: next phase of done[slot] to wait for
+        for (int s = 1; s < Tx; ++s) {
+            {
+                const unsigned target = (unsigned)(S * s);
+                const long long t0 = clock64();
+                bool ok;
+                do {
+                    ok = true;
+                    if (need) {
+                        unsigned v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pctr) : "memory");
+                        ok = v >= target;
+                    }
+                    if (!ok && clock64() - t0 > kSpinLimit) __trap();
+                } while (!__all_sync(0xffffffffu, ok));
+            }
+            if (lane == 0) {
                 // row of the raw operand: forward h_{t-1} = context row of the previous position of this direction;
                 // backward dG of the step processed just before
                 const int brow = BWD ? (dir == 0 ? Tx - s : s - 1) : (dir == 0 ? s - 1 : Tx - s);
-                flag_wait(ctr, nact * (unsigned)s);
                 asm volatile("fence.proxy.async;" ::: "memory");      // the operand was written by generic stores of other SMs
                 if (stamp && s == 8) ENC_STAMP(0);
                 for (int pr = 0; pr < npair; ++pr) {
@@ -263,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
                     }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 5 || warp == 6) {
         // ============================================================ MMA issuers
@@ -501,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
             named_bar_sync(1, kGateThreads);
             if (gtid == 0) {
                 if (stamp && s == 8) ENC_STAMP(10);
-                flag_arrive(ctr);                             // release: cumulative over the stores ordered before the barrier
+                flag_arrive(tctr);                            // release: cumulative over the stores ordered before the barrier
                 if (stamp && s == 8) ENC_STAMP(5);
             }
             // what no other CTA waits for
@@ -610,9 +624,9 @@ TcPlan plan(const nats_ctx* ctx, int n, int D, int pass) {
     p.smem = fixed + (size_t)p.NS * stage;
     const long long Kp = (p.Ktot + 3) / 4 * 4;
     p.lo_floats = (4LL * n * Kp + 3) / 4 * 4;
-    if (p.S * p.NG > kMaxWords) return p;
+    if (p.S * p.NG > kMaxWords || p.NT > 32) return p;
     p.slab_floats = 2LL * (2LL * p.NT * p.S * p.NG * p.BN * p.dpc);      // 64-bit words
-    p.counter_ints = 2LL * kCtrStride;
+    p.counter_ints = 2LL * p.NT * kCtrStride;
     p.ok = true;
     return p;
 }
@@ -666,7 +680,7 @@ long long enc_tc_scratch_floats(int n, int D) {
     const long long BN = n <= 32 ? 32 : 64;
     return 4LL * n * (3LL * D + 4) + 2LL * (2LL * 74 * 128 * BN) + 64;
 }
-long long enc_tc_counter_ints() { return 2LL * kCtrStride + 64; }
+long long enc_tc_counter_ints() { return 2LL * 32 * kCtrStride + 64; }
 
 int enc_tc_fwd(const nats_ctx* ctx, cudaStream_t st, const EncTcFwdArgs& g) {
     const TcPlan pl = plan(ctx, g.n, g.D, 0);

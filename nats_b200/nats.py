@@ -867,7 +867,7 @@ def _tile_ctx(ctx0, live_k):
 
 
 def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, stochastic=True, argmax=False,
-               use_unk=False, kl_factor=0, ctx_factor=0, state_factor=0, _scorer_factory=None):
+               use_unk=False, kl_factor=0, ctx_factor=0, state_factor=0, _scorer_factory=None, _trace=None):
     """Stochastic sampling or beam search with distraction re-ranking; same arguments, return values and
     hypothesis bookkeeping as the reference (nats.py:879-1076).  Candidate costs stay un-penalised (nats.py:1004);
     the three penalties only re-rank (nats.py:997-999)."""
@@ -924,6 +924,8 @@ def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, s
             cand_flat = cand_scores.flatten()
             if distract and ii > 0:
                 pen = scorer.penalties(cur[0], cur[1], cur[2], live_k, kl_factor, ctx_factor, state_factor)
+                if _trace is not None:
+                    _trace.append(dict(ii=ii, pen=numpy.array(pen)))
                 ranked = (cand_scores + pen[0][:, None] + pen[1][:, None] + pen[2][:, None]).flatten()
             else:
                 ranked = cand_flat
@@ -939,6 +941,8 @@ def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, s
             cand_flat = cand_scores.flatten()
             if distract and ii > 0:
                 pen = scorer.penalties(cur[0], cur[1], cur[2], live_k, kl_factor, ctx_factor, state_factor)
+                if _trace is not None:
+                    _trace.append(dict(ii=ii, pen=numpy.array(pen)))
                 ranked = (cand_scores + pen[0][:, None] + pen[1][:, None] + pen[2][:, None]).flatten()
                 ranks_flat = ranked.argsort()[:n_keep]
             else:

@@ -147,7 +147,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dcoef, hcoef.size() * 4)); CK(cudaMemcpy(dcoef, hcoef.data(), hcoef.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dcc, (size_t)Tmax * n * C * 4)); CK(cudaMemset(dcc, 0xff, (size_t)Tmax * n * C * 4));   // NaN fill: catches reads of unwritten rows
     CK(cudaMalloc(&dctx, (size_t)n * C * 4));
-    const long long scr = enc_tc_scratch_floats(&ctx, n, D), nbar = enc_tc_counter_ints(&ctx, n, D);
+    const long long scr = enc_tc_scratch_floats(n, D), nbar = enc_tc_counter_ints();
     CK(cudaMalloc(&dscr, scr * 4)); CK(cudaMemset(dscr, 0xff, scr * 4));
     CK(cudaMalloc(&dbar, nbar * 4)); CK(cudaMalloc(&ddbg, 128 * 8)); CK(cudaMemset(ddbg, 0, 128 * 8));
     EncTcFwdArgs a; memset(&a, 0, sizeof(a));
