@@ -37,6 +37,9 @@ namespace {
 
 using namespace tc;
 
+#ifndef ENC_TC_DBG
+#define ENC_TC_DBG 0        // timing experiments of tools/micro/enc_tc_test.cu (WRONG results): 1 = weight tile not advanced, 2 = no shared-memory-A MMAs, 3 = no tensor-memory-A MMAs
+#endif
 constexpr int kGateWarp0 = 7;           // warps 0-3: TMEM lane quadrants -> K-partial words; 4: flag poll + TMA producer;
 constexpr int kGateThreads = 256;       // 5 / 6: MMA issuers (A from shared / A from tensor memory); 7-14: gates
 constexpr int kThreads = kGateWarp0 * 32 + kGateThreads;
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map_raw[dir]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map_lo[dir]) : "memory");
-        for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < NS / 2; ++s) mbar_init(&full[s], 1);      // one per pair of ring stages
         for (int s = 0; s < NS / 2; ++s) mbar_init(&done[s], 2);      // both MMA issuers commit
         mbar_init(&accum_bar, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    unsigned* tctr = a.bar + (dir * NT + tile) * kCtrStride;      // arrivals of this row tile's CTAs (S per step)
+    unsigned* tctr = a.bar + (dir * NT + tile) * kCtrStride;      // arrivals of this row tile's gate warps (S * 8 per step)
     const bool stamp = a.dbg != nullptr && blockIdx.x == 0;
 #define ENC_STAMP(i) do { a.dbg[i] = gtimer(); a.dbg[32 + (i)] = (unsigned long long)clock64(); } while (0)
 
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
         uint32_t dpar = 0;                                   // parity bit per pair slot: next phase of done[slot] to wait for
         for (int s = 1; s < Tx; ++s) {
             {
-                const unsigned target = (unsigned)(S * s);
+                const unsigned target = (unsigned)(S * (kGateThreads / 32) * s);
                 const long long t0 = clock64();
                 bool ok;
                 do {
@@ -263,15 +266,15 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
                         mbar_wait_b(&done[slot], (dpar >> slot) & 1u);
                         dpar ^= 1u << slot;
                     }
+                    const int nb = min(2, nkb - 2 * pr);             // k-blocks of this pair (the last pair may be single)
+                    mbar_expect_tx(&full[slot], (uint32_t)nb * kStage);
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const int kb = 2 * pr + q;
-                        if (kb < nkb) {
-                            const int st = 2 * slot + q;
-                            mbar_expect_tx(&full[st], kStage);
-                            const uint32_t dst = sRing + (uint32_t)st * kStage;
-                            tma_load_3d(dst, &a.map_raw[dir], &full[st], kbeg + 32 * kb, 0, brow);
-                            tma_load_3d(dst + BN * 128u, &a.map_lo[dir], &full[st], kbeg + 32 * kb, 0, (s - 1) & 1);
+                        if (q < nb) {
+                            const int kb = 2 * pr + q;
+                            const uint32_t dst = sRing + (uint32_t)(2 * slot + q) * kStage;
+                            tma_load_3d(dst, &a.map_raw[dir], &full[slot], kbeg + 32 * kb, 0, brow);
+                            tma_load_3d(dst + BN * 128u, &a.map_lo[dir], &full[slot], kbeg + 32 * kb, 0, (s - 1) & 1);
                         }
                     }
                 }
@@ -294,39 +297,47 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
             const uint32_t acc0 = tmem, acc1 = tmem + 2u * BN, acc2 = tmem + kAcc2;
             const uint64_t adesc0 = desc_kmajor(sA), bdesc0 = desc_kmajor(sRing);
             const int ncommit = max(0, npair - NP);          // pairs whose stages are reused within a step
-            const int nkb_l = nkb, NS_l = NS, Tx_l = Tx;
+            const int nkb_l = nkb, Tx_l = Tx;
             const bool ss = warp == 5;
-            uint32_t fpar = 0;                               // parity bit per stage: next phase of full[stage]
+            uint32_t fpar = 0;                               // parity bit per pair slot: next phase of full[slot]
+            const int npair_l = npair, NP_l = NP;
+            const bool odd = (nkb_l & 1) != 0;               // the last pair holds a single k-block
             for (int s = 1; s < Tx_l; ++s) {
                 uint64_t adesc = adesc0;
                 uint32_t alo = tmem + kLoCol;
-                int st = 0;
-#define ENC_MMA_BLOCK(FIRST)                                                                                         \
-    {                                                                                                                \
-        mbar_wait_b(&full[st], (fpar >> st) & 1u);                                                                   \
-        fpar ^= 1u << st;                                                                                            \
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                              \
-        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)st * (kStage >> 4));                                    \
-        if (ss) {                                                                                                    \
-            umma_tf32(acc0, adesc, bdesc, idesc2, (FIRST) ? 0u : 1u);                                                \
-            umma_tf32(acc1, adesc + 2, bdesc + 2, idesc2, (FIRST) ? 0u : 1u);                                        \
-            umma_tf32(acc0, adesc + 4, bdesc + 4, idesc2, 1u);                                                       \
-            umma_tf32(acc1, adesc + 6, bdesc + 6, idesc2, 1u);                                                       \
-        } else {                                                                                                     \
-            umma_tf32_ts(acc2, alo, bdesc, idesc1, (FIRST) ? 0u : 1u);                                               \
-            umma_tf32_ts(acc2, alo + 8, bdesc + 2, idesc1, 1u);                                                      \
-            umma_tf32_ts(acc2, alo + 16, bdesc + 4, idesc1, 1u);                                                     \
-            umma_tf32_ts(acc2, alo + 24, bdesc + 6, idesc1, 1u);                                                     \
+                int slot = 0;
+                // one full barrier per PAIR of k-blocks: the per-block bookkeeping of this single thread (wait, parity,
+                // descriptor arithmetic: ~10 cycles per dependent scalar instruction) costs as much as the MMAs themselves
+#define ENC_MMA_4(FIRST, AD, AL, BD)                                                                                 \
+    if (ss) {                                                                                                        \
+        if (ENC_TC_DBG != 2) {                                                                                       \
+            umma_tf32(acc0, (AD), (BD), idesc2, (FIRST) ? 0u : 1u);                                                  \
+            umma_tf32(acc1, (AD) + 2, (BD) + 2, idesc2, (FIRST) ? 0u : 1u);                                          \
+            umma_tf32(acc0, (AD) + 4, (BD) + 4, idesc2, 1u);                                                         \
+            umma_tf32(acc1, (AD) + 6, (BD) + 6, idesc2, 1u);                                                         \
         }                                                                                                            \
-        adesc += 1024; alo += 32;                                                                                    \
+    } else if (ENC_TC_DBG != 3) {                                                                                    \
+        umma_tf32_ts(acc2, (AL), (BD), idesc1, (FIRST) ? 0u : 1u);                                                   \
+        umma_tf32_ts(acc2, (AL) + 8, (BD) + 2, idesc1, 1u);                                                          \
+        umma_tf32_ts(acc2, (AL) + 16, (BD) + 4, idesc1, 1u);                                                         \
+        umma_tf32_ts(acc2, (AL) + 24, (BD) + 6, idesc1, 1u);                                                         \
     }
-                ENC_MMA_BLOCK(true)
-                if (stamp && ss && s == 8) ENC_STAMP(1);
-                st = 1;
-                for (int kb = 1; kb < nkb_l; ++kb) {
-                    ENC_MMA_BLOCK(false)
-                    if ((kb & 1) && (kb >> 1) < ncommit) umma_commit(&done[(kb >> 1) % NP]);
-                    st = (st + 1 == NS_l) ? 0 : st + 1;
+                for (int pr = 0; pr < npair_l; ++pr) {
+                    mbar_wait_b(&full[slot], (fpar >> slot) & 1u);
+                    fpar ^= 1u << slot;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)slot * (2u * (kStage >> 4)));
+                    if (pr == 0) {
+                        ENC_MMA_4(true, adesc, alo, bdesc)
+                        if (stamp && ss && s == 8) ENC_STAMP(1);
+                    } else {
+                        ENC_MMA_4(false, adesc, alo, bdesc)
+                    }
+                    if (!(odd && pr == npair_l - 1)) { ENC_MMA_4(false, adesc + 1024, alo + 32, bdesc + (kStage >> 4)) }
+                    if (ENC_TC_DBG != 1) adesc += 2048;
+                    alo += 64;
+                    if (pr < ncommit) umma_commit(&done[slot]);
+                    slot = (slot + 1 == NP_l) ? 0 : slot + 1;
                 }
                 umma_commit(&accum_bar);
                 if (stamp && ss && s == 8) ENC_STAMP(2);
@@ -512,11 +523,12 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
                 }
             }
             if (stamp && s == 8 && gtid == 0) ENC_STAMP(9);
-            named_bar_sync(1, kGateThreads);
-            if (gtid == 0) {
-                if (stamp && s == 8) ENC_STAMP(10);
-                flag_arrive(tctr);                            // release: cumulative over the stores ordered before the barrier
-                if (stamp && s == 8) ENC_STAMP(5);
+            // every gate warp releases its own stores (no CTA-wide barrier in front of the fence): the tile counter counts
+            // S * 8 arrivals per step
+            __syncwarp();
+            if (lane == 0) {
+                flag_arrive(tctr);                            // release: cumulative over the warp's stores ordered before __syncwarp
+                if (stamp && s == 8 && gtid == 0) ENC_STAMP(5);
             }
             // what no other CTA waits for
 #pragma unroll

@@ -231,9 +231,9 @@ int main(int argc, char** argv) {
         const unsigned long long* h = hd + 64 * k;
         const double mhz = (double)(h[32 + 5] - h[32 + 0]) / (double)(h[5] - h[0]) * 1000.0;
         printf("%s step 8, CTA 0, SM clock %.0f MHz; ns after the direction flag was seen:\n", k ? "bwd" : "fwd", mhz);
-        printf("   first k-block issued %lld | last MMA issued %lld | accum ready %lld | tmem read + partial stores %lld | partials complete %lld | gates+stores %lld | bar %lld | arrive %lld\n",
+        printf("   first k-block issued %lld | last MMA issued %lld | accum ready %lld | tmem read + partial stores %lld | partials complete %lld | gates+stores %lld | arrive %lld\n",
                (long long)(h[1] - h[0]), (long long)(h[2] - h[0]), (long long)(h[3] - h[0]), (long long)(h[6] - h[0]),
-               (long long)(h[4] - h[0]), (long long)(h[9] - h[0]), (long long)(h[10] - h[0]), (long long)(h[5] - h[0]));
+               (long long)(h[4] - h[0]), (long long)(h[9] - h[0]), (long long)(h[5] - h[0]));
     }
     return pass && passb ? 0 : 3;
 }
