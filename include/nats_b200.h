@@ -83,6 +83,21 @@ int nats_train_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const
                    const int64_t* x, const float* x_mask, const int64_t* y, const float* y_mask,
                    int Tx, int Ty, int B, void* ws, int64_t ws_bytes, float scale, float* grads);
 
+/* nats_train_bwd in two halves, for overlapping the data-parallel all-reduce with the backward itself:
+ *   _begin  = zero grads, cost tail, readout + decoder-scan backward: on return (in stream order) the slice
+ *             grads[nats_grad_split(dims) .. total_floats + NATS_GRAD_TAIL) -- ff_state, decoder, readout parameters and
+ *             the cost slot, ~65 % of the buffer -- is FINAL and may be all-reduced while _finish runs;
+ *   _finish = encoder backward (both recurrences + their weight gradients + the source-side Wemb scatter): completes
+ *             grads[0 .. nats_grad_split(dims)) = Wemb, encoder, encoder_r.
+ * _begin followed by _finish == nats_train_bwd. */
+int64_t nats_grad_split(const nats_dims_t* dims);
+int nats_train_bwd_begin(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                         const int64_t* x, const float* x_mask, const int64_t* y, const float* y_mask,
+                         int Tx, int Ty, int B, void* ws, int64_t ws_bytes, float scale, float* grads);
+int nats_train_bwd_finish(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
+                          const int64_t* x, const float* x_mask, const int64_t* y, const float* y_mask,
+                          int Tx, int Ty, int B, void* ws, int64_t ws_bytes, float scale, float* grads);
+
 /* Finer-grained pieces of the same graph; all operate on the same workspace. */
 int nats_encoder_fwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
                      const int64_t* x, const float* x_mask /* NULL = all ones */, int Tx, int Ty, int B,

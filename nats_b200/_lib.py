@@ -35,6 +35,11 @@ SIGNATURES = {
     'nats_train_fwd': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P]),
     'nats_train_bwd': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64,
                                c_float, _P]),
+    'nats_grad_split': (c_int64, [POINTER(Dims)]),
+    'nats_train_bwd_begin': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64,
+                                     c_float, _P]),
+    'nats_train_bwd_finish': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64,
+                                      c_float, _P]),
     'nats_encoder_fwd': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, c_int, c_int, c_int, _P, c_int64]),
     'nats_decoder_scan_fwd': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64]),
     'nats_readout_nll_fwd': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P]),

@@ -295,9 +295,14 @@ int nats_train_fwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const
     return 0;
 }
 
-int nats_train_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params, const int64_t* x,
-                   const float* x_mask, const int64_t* y, const float* y_mask, int Tx, int Ty, int B, void* ws,
-                   int64_t ws_bytes, float scale, float* grads) {
+int64_t nats_grad_split(const nats_dims_t* dims) {
+    if (check_dims(dims) != 0) return -1;
+    return param_offsets(*dims).ff_state_W;      // [Wemb | encoder | encoder_r] come first in the flat layout
+}
+
+int nats_train_bwd_begin(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params, const int64_t* x,
+                         const float* x_mask, const int64_t* y, const float* y_mask, int Tx, int Ty, int B, void* ws,
+                         int64_t ws_bytes, float scale, float* grads) {
     NATS_TRAIN_PROLOGUE();
     NATS_REQUIRE(x && x_mask && y && y_mask && grads && params, "null argument");
     const ParamOff o = param_offsets(*dims);
@@ -305,8 +310,23 @@ int nats_train_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const
     NATS_TRY(cost_reduce(st, w.rowcost, Ty, B, nullptr, scale, grads + o.total));
     NATS_TRY(train_readout_bwd(ctx, st, *dims, params, y, y_mask, Ty, B, w, scale, grads));
     NATS_TRY(train_decoder_bwd(ctx, st, *dims, params, y, x_mask, y_mask, Tx, Ty, B, w, grads));
-    NATS_TRY(train_encoder_bwd(ctx, st, *dims, params, x, x_mask, y, Tx, Ty, B, w, grads));
     return 0;
+}
+
+int nats_train_bwd_finish(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params, const int64_t* x,
+                          const float* x_mask, const int64_t* y, const float* y_mask, int Tx, int Ty, int B, void* ws,
+                          int64_t ws_bytes, float scale, float* grads) {
+    (void)scale; (void)y_mask;
+    NATS_TRAIN_PROLOGUE();
+    NATS_REQUIRE(x && x_mask && y && grads && params, "null argument");
+    return train_encoder_bwd(ctx, st, *dims, params, x, x_mask, y, Tx, Ty, B, w, grads);
+}
+
+int nats_train_bwd(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params, const int64_t* x,
+                   const float* x_mask, const int64_t* y, const float* y_mask, int Tx, int Ty, int B, void* ws,
+                   int64_t ws_bytes, float scale, float* grads) {
+    NATS_TRY(nats_train_bwd_begin(ctx, stream, dims, params, x, x_mask, y, y_mask, Tx, Ty, B, ws, ws_bytes, scale, grads));
+    return nats_train_bwd_finish(ctx, stream, dims, params, x, x_mask, y, y_mask, Tx, Ty, B, ws, ws_bytes, scale, grads);
 }
 
 const float* nats_train_ws_view(const nats_dims_t* dims, int Tx, int Ty, int B, void* ws, const char* name) {

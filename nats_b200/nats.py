@@ -321,54 +321,126 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+def _bucket(n, q):
+    """round n up to a multiple of q (q <= 1: no bucketing)"""
+    return int(n) if q <= 1 else ((int(n) + q - 1) // q) * q
+
+
+class _Arena(object):
+    """Storage shared by every plan of a ModelGraph: ONE workspace sized for the largest shape seen, one packed device
+    input buffer (x | y | x_mask | y_mask) and its pinned host mirror -> one H2D copy per step.  Plans are views; when the
+    arena has to grow (a larger shape than any before) every captured CUDA graph is dropped with the old addresses."""
+
+    def __init__(self, model):
+        self.model = model
+        self.ws = None
+        self.ws_bytes = 0
+        self.inp = None         # uint8 device buffer
+        self.pin = None         # uint8 pinned host mirror
+        self.inp_bytes = 0
+        self.version = 0
+
+    @staticmethod
+    def input_layout(Tx, Ty, B):
+        ox = 0
+        oy = ox + Tx * B * 8
+        oxm = oy + Ty * B * 8
+        oym = oxm + Tx * B * 4
+        return ox, oy, oxm, oym, oym + Ty * B * 4
+
+    def reserve(self, Tx, Ty, B):
+        eng = self.model.engine
+        torch = eng.torch
+        need_ws = int(eng.lib.nats_train_workspace_bytes(ctypes.byref(self.model.dims), Tx, Ty, B))
+        if need_ws <= 0:
+            raise NatsB200Error('nats_train_workspace_bytes failed')
+        need_in = self.input_layout(Tx, Ty, B)[4]
+        grown = False
+        if need_ws > self.ws_bytes:
+            self.ws = None
+            self.ws = torch.empty(need_ws, dtype=torch.uint8, device=eng.device)
+            self.ws_bytes = need_ws
+            grown = True
+        if need_in > self.inp_bytes:
+            self.inp = torch.zeros(need_in, dtype=torch.uint8, device=eng.device)
+            self.pin = torch.zeros(need_in, dtype=torch.uint8).pin_memory()
+            self.inp_bytes = need_in
+            grown = True
+        if grown:
+            self.version += 1
+        return need_ws
+
+
 class _TrainPlan(object):
-    """Everything bound to one (Tx, Ty, B) shape: static input buffers, workspace, optional CUDA graph."""
+    """Everything bound to one (Tx, Ty, B) shape: views of the arena's input buffers and workspace, optional CUDA graphs."""
 
     def __init__(self, model, Tx, Ty, B):
         torch = model.engine.torch
-        eng = model.engine
+        arena = model.arena
         self.shape = (Tx, Ty, B)
-        dev = eng.device
-        self.x = torch.zeros((Tx, B), dtype=torch.int64, device=dev)
-        self.y = torch.zeros((Ty, B), dtype=torch.int64, device=dev)
-        self.xm = torch.zeros((Tx, B), dtype=torch.float32, device=dev)
-        self.ym = torch.zeros((Ty, B), dtype=torch.float32, device=dev)
-        self.hx = torch.zeros((Tx, B), dtype=torch.int64).pin_memory()
-        self.hy = torch.zeros((Ty, B), dtype=torch.int64).pin_memory()
-        self.hxm = torch.zeros((Tx, B), dtype=torch.float32).pin_memory()
-        self.hym = torch.zeros((Ty, B), dtype=torch.float32).pin_memory()
-        self.cost = torch.zeros((B,), dtype=torch.float32, device=dev)
-        nbytes = eng.lib.nats_train_workspace_bytes(ctypes.byref(model.dims), Tx, Ty, B)
-        if nbytes <= 0:
-            raise NatsB200Error('nats_train_workspace_bytes failed')
-        self.ws_bytes = int(nbytes)
-        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.ws_bytes = arena.reserve(Tx, Ty, B)
+        self.arena_version = arena.version
+        self.ws = arena.ws
+        ox, oy, oxm, oym, end = arena.input_layout(Tx, Ty, B)
+        self.in_bytes = end
+
+        def views(buf):
+            return (buf[ox:oy].view(torch.int64).view(Tx, B), buf[oy:oxm].view(torch.int64).view(Ty, B),
+                    buf[oxm:oym].view(torch.float32).view(Tx, B), buf[oym:end].view(torch.float32).view(Ty, B))
+        self.x, self.y, self.xm, self.ym = views(arena.inp)
+        self.hx, self.hy, self.hxm, self.hym = [t.numpy() for t in views(arena.pin)]      # numpy views of the pinned mirror
+        self.dev_in, self.pin_in = arena.inp[:end], arena.pin[:end]
+        self.cost = torch.zeros((B,), dtype=torch.float32, device=model.engine.device)
         self.graph_fwd = None      # forward only (f_log_probs)
-        self.graph_fb = None       # forward + backward (data-parallel: the allreduce sits between fb and post)
+        self.graph_fb = None       # forward + first half of the backward (data-parallel)
+        self.graph_fb2 = None      # second half of the backward (encoder), overlapped with the first all-reduce
         self.graph_post = None     # L2 / clip / optimiser accumulators
-        self.graph_step = None     # single GPU: fb + post in one graph
+        self.graph_step = None     # single GPU: forward + backward + post in one graph
         self.uses = 0
 
     def stage(self, x, x_mask, y, y_mask):
-        import torch as _t
-        self.hx.copy_(_t.from_numpy(numpy.ascontiguousarray(x, dtype='int64')))
-        self.hxm.copy_(_t.from_numpy(numpy.ascontiguousarray(x_mask, dtype='float32')))
-        self.hy.copy_(_t.from_numpy(numpy.ascontiguousarray(y, dtype='int64')))
-        self.hym.copy_(_t.from_numpy(numpy.ascontiguousarray(y_mask, dtype='float32')))
-        self.x.copy_(self.hx, non_blocking=True)
-        self.xm.copy_(self.hxm, non_blocking=True)
-        self.y.copy_(self.hy, non_blocking=True)
-        self.ym.copy_(self.hym, non_blocking=True)
+        """host arrays (any shape <= the plan's: the rest is zero padding, masked out) -> pinned mirror -> ONE H2D copy"""
+        Tx, Ty, B = self.shape
+        for dst, src in ((self.hx, x), (self.hxm, x_mask), (self.hy, y), (self.hym, y_mask)):
+            t = src.shape[0]
+            dst[:t] = src
+            if t < dst.shape[0]:
+                dst[t:] = 0
+        self.dev_in.copy_(self.pin_in, non_blocking=True)
 
     def h2d_bytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.hx, self.hxm, self.hy, self.hym))
+        return int(self.in_bytes)
+
+
+class LazyCost(object):
+    """The scalar cost of a step whose device->host read is still in flight (pinned buffer + event).  float() / numpy
+    conversion waits for it; the training loop of the reference converts immediately, a pipelined caller (bench.py)
+    converts one step later and keeps the GPU queue full."""
+
+    def __init__(self, host_buf, event, extra=0.0):
+        self._buf, self._ev, self._extra, self._v = host_buf, event, extra, None
+
+    def value(self):
+        if self._v is None:
+            self._ev.synchronize()
+            self._v = numpy.float32(float(self._buf[0]) + self._extra)
+        return self._v
+
+    def __float__(self):
+        return float(self.value())
+
+    def __array__(self, dtype=None, copy=None):
+        return numpy.asarray(self.value(), dtype=dtype)
+
+    def __repr__(self):
+        return repr(self.value())
 
 
 class ModelGraph(object):
     """What build_model returns in place of the symbolic `cost` (nats.py:772): the training graph bound to a
     device store.  f_log_probs / f_cost / gradients are produced from it by train() and the optimiser factories."""
 
-    MAX_PLANS = 4
+    MAX_PLANS = 64            # plans are views + CUDA graphs (the storage is shared): cheap
 
     def __init__(self, tparams, options):
         self.tparams = tparams
@@ -380,11 +452,22 @@ class ModelGraph(object):
         self.clip_c = -1.
         self.is_mean = False
         self._plans = OrderedDict()
+        self.arena = _Arena(self)
         self.use_graphs = os.environ.get('NATS_CUDA_GRAPHS', '1') != '0'
+        # shape buckets: padded source / target lengths are rounded up so that ragged batches reuse captured graphs
+        # (zero-padded positions are masked out: cost and gradients do not change, nats.py:354,518,565,770)
+        self.bucket_tx = int(os.environ.get('NATS_BUCKET_TX', '8'))
+        self.bucket_ty = int(os.environ.get('NATS_BUCKET_TY', '5'))
+        self.lazy_cost = False
+        self.overlap_allreduce = os.environ.get('NATS_OVERLAP_ALLREDUCE', '1') != '0'
         torch = self.engine.torch
         self.grads = torch.zeros(tparams.total + _lib.GRAD_TAIL, dtype=torch.float32, device=self.engine.device)
         self.stats = torch.zeros(8, dtype=torch.float32, device=self.engine.device)
         self.rank, self.world = parallel.world()
+        self.split = int(self.engine.lib.nats_grad_split(ctypes.byref(self.dims)))
+        self._side = None
+        self._cost_ring = None
+        self._cost_slot = 0
 
     # -- reference idiom: cost = cost.mean() (nats.py:1323)
     def mean(self):
@@ -392,33 +475,45 @@ class ModelGraph(object):
         g.is_mean = True
         return g
 
+    def reserve(self, Tx, Ty, B):
+        """size the shared storage for the largest batch that will be seen (train() knows maxlen and batch_size), so
+        that no later plan has to grow it (growing drops every captured graph)"""
+        self.arena.reserve(_bucket(Tx, self.bucket_tx), _bucket(Ty, self.bucket_ty), B)
+
     def plan(self, Tx, Ty, B):
-        key = (Tx, Ty, B)
+        key = (_bucket(Tx, self.bucket_tx), _bucket(Ty, self.bucket_ty), B)
         p = self._plans.get(key)
+        if p is not None and p.arena_version != self.arena.version:
+            self._plans.clear()               # the arena moved: every captured graph holds stale addresses
+            p = None
         if p is None:
             while len(self._plans) >= self.MAX_PLANS:
                 self._plans.popitem(last=False)
-            p = _TrainPlan(self, Tx, Ty, B)
+            v0 = self.arena.version
+            p = _TrainPlan(self, *key)
+            if self.arena.version != v0:
+                self._plans.clear()
             self._plans[key] = p
         else:
             self._plans.move_to_end(key)
         return p
 
     # -- raw enqueue helpers (no host sync)
+    def _train_args(self, p):
+        Tx, Ty, B = p.shape
+        return (self.engine.ctx, self.engine.stream(), ctypes.byref(self.dims), _ptr(self.tparams.flat), _ptr(p.x), _ptr(p.xm),
+                _ptr(p.y), _ptr(p.ym), Tx, Ty, B, _ptr(p.ws), p.ws_bytes)
+
     def enqueue_fwd(self, p):
         eng = self.engine
-        Tx, Ty, B = p.shape
-        _lib.check(eng.lib.nats_train_fwd(eng.ctx, eng.stream(), ctypes.byref(self.dims), _ptr(self.tparams.flat),
-                                          _ptr(p.x), _ptr(p.xm), _ptr(p.y), _ptr(p.ym), Tx, Ty, B, _ptr(p.ws),
-                                          p.ws_bytes, _ptr(p.cost)), 'nats_train_fwd')
+        _lib.check(eng.lib.nats_train_fwd(*(self._train_args(p) + (_ptr(p.cost),))), 'nats_train_fwd')
         eng.launches += 1
 
-    def enqueue_bwd(self, p, scale):
+    def enqueue_bwd(self, p, scale, part=0):
+        """part 0: whole backward; 1: readout + decoder (grads[split:] final); 2: encoder (grads[:split] final)"""
         eng = self.engine
-        Tx, Ty, B = p.shape
-        _lib.check(eng.lib.nats_train_bwd(eng.ctx, eng.stream(), ctypes.byref(self.dims), _ptr(self.tparams.flat),
-                                          _ptr(p.x), _ptr(p.xm), _ptr(p.y), _ptr(p.ym), Tx, Ty, B, _ptr(p.ws),
-                                          p.ws_bytes, ctypes.c_float(scale), _ptr(self.grads)), 'nats_train_bwd')
+        fn = (eng.lib.nats_train_bwd, eng.lib.nats_train_bwd_begin, eng.lib.nats_train_bwd_finish)[part]
+        _lib.check(fn(*(self._train_args(p) + (ctypes.c_float(scale), _ptr(self.grads)))), 'nats_train_bwd')
         eng.launches += 1
 
     def enqueue_clip(self):
@@ -429,13 +524,13 @@ class ModelGraph(object):
         eng.launches += 1
 
     def _run(self, p, attr, body):
-        """run `body` eagerly the first two times a shape is seen, then capture + replay it as a CUDA graph"""
+        """run `body` eagerly the first time a shape is seen, then capture + replay it as a CUDA graph"""
         torch = self.engine.torch
         g = getattr(p, attr)
         if g is not None:
             g.replay()
             return
-        if self.use_graphs and p.uses >= 2:
+        if self.use_graphs and p.uses >= 1:
             torch.cuda.synchronize(self.engine.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -461,34 +556,74 @@ class ModelGraph(object):
             c += self.decay_c * float((self.tparams.flat.double() ** 2).sum().item())
         return numpy.float32(c)
 
-    def grad_step(self, x, x_mask, y, y_mask, after_grads):
-        """forward + backward (+ allreduce) + L2/clip + `after_grads()` (the optimiser's accumulator update);
-        returns the scalar cost like f_grad_shared (nats.py:1160)."""
+    def _read_cost(self):
+        """device->host read of the step result: async copy into a pinned ring slot + event"""
         torch = self.engine.torch
+        if self._cost_ring is None:
+            self._cost_ring = [(torch.zeros(2, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+        buf, ev = self._cost_ring[self._cost_slot]
+        self._cost_slot = (self._cost_slot + 1) % len(self._cost_ring)
+        buf[:1].copy_(self.grads[self.tparams.total:self.tparams.total + 1], non_blocking=True)
+        if self.decay_c > 0.:
+            buf[1:2].copy_(self.stats[1:2], non_blocking=True)
+        ev.record()
+        hb = buf.numpy()
+
+        class _B(object):           # buf[0] (+ decay_c * ||p||^2 once the event has completed)
+            def __getitem__(s, i):
+                return hb[0] + (self.decay_c * hb[1] if self.decay_c > 0. else 0.0)
+        return LazyCost(_B(), ev)
+
+    def grad_step(self, x, x_mask, y, y_mask, after_grads, global_batch=None):
+        """forward + backward (+ allreduce) + L2/clip + `after_grads()` (the optimiser's accumulator update);
+        returns the scalar cost like f_grad_shared (nats.py:1160).  `global_batch`: number of sentence pairs of the
+        whole data-parallel step (default: local batch x world size).  x = None: this rank's shard is empty; it only
+        contributes zeros to the all-reduce."""
+        torch = self.engine.torch
+        world = self.world
+        if x is None:
+            assert world > 1, 'empty batch'
+            self.grads.zero_()
+            parallel.allreduce_flat(self.grads)
+            self.enqueue_clip()
+            after_grads()
+            c = self._read_cost()
+            return c if self.lazy_cost else c.value()
         p = self.plan(x.shape[0], y.shape[0], x.shape[1])
         p.stage(x, x_mask, y, y_mask)
         B = x.shape[1]
-        scale = parallel.grad_scale(B, self.world)   # d mean(cost) over the GLOBAL batch (nats.py:1323)
-
-        def fwd_bwd():
-            self.enqueue_fwd(p)
-            self.enqueue_bwd(p, scale)
+        scale = parallel.grad_scale(B, world, global_batch)   # d mean(cost) over the GLOBAL batch (nats.py:1323)
 
         def post():
             self.enqueue_clip()
             after_grads()
 
-        if self.world == 1:
-            self._run(p, 'graph_step', lambda: (fwd_bwd(), post()))
-        else:
-            self._run(p, 'graph_fb', fwd_bwd)
+        if world == 1:
+            self._run(p, 'graph_step', lambda: (self.enqueue_fwd(p), self.enqueue_bwd(p, scale), post()))
+        elif not self.overlap_allreduce:
+            self._run(p, 'graph_fb', lambda: (self.enqueue_fwd(p), self.enqueue_bwd(p, scale)))
             parallel.allreduce_flat(self.grads)               # ONE collective: gradients + cost tail
             self._run(p, 'graph_post', post)
+        else:
+            # the decoder / readout / ff_state gradients (grads[split:], ~65 % of the buffer, + the cost slot) are final
+            # before the encoder backward starts: their all-reduce runs on a side stream UNDER the encoder backward,
+            # only the encoder slice is reduced after it
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.engine.device)
+            main = torch.cuda.current_stream(self.engine.device)
+            self._run(p, 'graph_fb', lambda: (self.enqueue_fwd(p), self.enqueue_bwd(p, scale, 1)))
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                w1 = parallel.allreduce_flat(self.grads[self.split:], async_op=True)
+            self._run(p, 'graph_fb2', lambda: self.enqueue_bwd(p, scale, 2))
+            parallel.allreduce_flat(self.grads[:self.split])
+            if w1 is not None:
+                w1.wait()
+            main.wait_stream(self._side)
+            self._run(p, 'graph_post', post)
         p.uses += 1
-        cost = float(self.grads[self.tparams.total].item())   # device->host read of the step result
-        if self.decay_c > 0.:
-            cost += self.decay_c * float(self.stats[1].item())
-        return numpy.float32(cost)
+        c = self._read_cost()
+        return c if self.lazy_cost else c.value()
 
 
 def build_model(tparams, options):
@@ -533,8 +668,8 @@ def adadelta(lr, tparams, grads, inp, cost, epsilon=1e-6, rho=0.95):
                    'nats_adadelta_grad_shared')
         eng.launches += 1
 
-    def f_grad_shared(x, x_mask, y, y_mask):
-        return graph.grad_step(x, x_mask, y, y_mask, accum)
+    def f_grad_shared(x, x_mask, y, y_mask, global_batch=None):
+        return graph.grad_step(x, x_mask, y, y_mask, accum, global_batch=global_batch)
 
     def f_update(lr_value=None):
         _lib.check(eng.lib.nats_adadelta_update(eng.ctx, eng.stream(), n, _ptr(tparams.flat), _ptr(graph.grads),
@@ -553,19 +688,19 @@ def adam(lr, tparams, grads, inp, cost):
     eng = graph.engine
     m, v = _zeros_like_flat(graph), _zeros_like_flat(graph)
     n = tparams.total
-    step = [0]
+    step = numpy.zeros(1, dtype='int64')
 
-    def f_grad_shared(x, x_mask, y, y_mask):
-        return graph.grad_step(x, x_mask, y, y_mask, lambda: None)
+    def f_grad_shared(x, x_mask, y, y_mask, global_batch=None):
+        return graph.grad_step(x, x_mask, y, y_mask, lambda: None, global_batch=global_batch)
 
     def f_update(lr_value=None):
         _lib.check(eng.lib.nats_adam_update(eng.ctx, eng.stream(), n, _ptr(tparams.flat), _ptr(graph.grads),
-                                            _ptr(m), _ptr(v), step[0]), 'nats_adam_update')
+                                            _ptr(m), _ptr(v), int(step[0])), 'nats_adam_update')
         eng.launches += 1
         step[0] += 1
         return []
 
-    f_grad_shared.state = dict(m=m, v=v)
+    f_grad_shared.state = dict(m=m, v=v, step=step)
     return f_grad_shared, f_update
 
 
@@ -580,8 +715,8 @@ def rmsprop(lr, tparams, grads, inp, cost):
                                                     _ptr(rg2)), 'nats_rmsprop_grad_shared')
         eng.launches += 1
 
-    def f_grad_shared(x, x_mask, y, y_mask):
-        return graph.grad_step(x, x_mask, y, y_mask, accum)
+    def f_grad_shared(x, x_mask, y, y_mask, global_batch=None):
+        return graph.grad_step(x, x_mask, y, y_mask, accum, global_batch=global_batch)
 
     def f_update(lr_value=None):
         _lib.check(eng.lib.nats_rmsprop_update(eng.ctx, eng.stream(), n, _ptr(tparams.flat), _ptr(graph.grads),
@@ -598,8 +733,8 @@ def sgd(lr, tparams, grads, inp, cost):
     provided here with the common 5-argument form: p <- p - lr * g."""
     graph = grads
 
-    def f_grad_shared(x, x_mask, y, y_mask):
-        return graph.grad_step(x, x_mask, y, y_mask, lambda: None)
+    def f_grad_shared(x, x_mask, y, y_mask, global_batch=None):
+        return graph.grad_step(x, x_mask, y, y_mask, lambda: None, global_batch=global_batch)
 
     def f_update(lr_value):
         tparams.flat.add_(graph.grads[:tparams.total], alpha=-float(lr_value))
@@ -626,6 +761,26 @@ class DeviceBackedArray(numpy.ndarray):
 
     def __array_finalize__(self, obj):
         self._nats_handle = getattr(obj, '_nats_handle', None)
+
+    # the handle stands for "these values are the encoder context on the device": anything computed FROM the array
+    # (ufuncs) is a plain ndarray, and writing into the array drops the handle
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        plain = [numpy.asarray(i) if isinstance(i, DeviceBackedArray) else i for i in inputs]
+        if 'out' in kwargs:
+            for o in kwargs['out']:
+                if isinstance(o, DeviceBackedArray):
+                    o._nats_handle = None
+            kwargs['out'] = tuple(numpy.asarray(o) if isinstance(o, DeviceBackedArray) else o for o in kwargs['out'])
+        return getattr(ufunc, method)(*plain, **kwargs)
+
+    def __setitem__(self, key, value):
+        self._nats_handle = None
+        b = self.base
+        while isinstance(b, numpy.ndarray):                 # writing through a view invalidates the owner as well
+            if isinstance(b, DeviceBackedArray):
+                b._nats_handle = None
+            b = b.base
+        numpy.ndarray.__setitem__(self, key, value)
 
 
 class _CtxHandle(object):
@@ -1025,16 +1180,79 @@ def _words(ids, worddicts_r):
     return ' '.join(out)
 
 
+def _prefetched(gen, depth):
+    """run generator `gen` in a background thread, `depth` items ahead (0: inline).  The consumer spends its time inside
+    cudaStreamSynchronize (GIL released), so the next batch is padded and ready when the step returns."""
+    if depth <= 0:
+        for item in gen:
+            yield item
+        return
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    END = object()
+
+    def work():
+        try:
+            for item in gen:
+                q.put(item)
+            q.put(END)
+        except BaseException as e:          # surfaced in the consumer
+            q.put(e)
+    th = threading.Thread(target=work, daemon=True)
+    th.start()
+    while True:
+        item = q.get()
+        if item is END:
+            break
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+    th.join()
+
+
+def save_optimizer_state_file(path, f_grad_shared):
+    """optimiser accumulators (flat buffers, packed layout of the parameter store) next to the model file; the model
+    npz / pkl keep the reference's key set (nats.py:1427-1435)."""
+    st = getattr(f_grad_shared, 'state', None) or {}
+    out = {}
+    for k, v in st.items():
+        out[k] = v.detach().cpu().numpy() if hasattr(v, 'detach') else numpy.asarray(v)
+    numpy.savez(path, **out)
+
+
+def load_optimizer_state(path, f_grad_shared):
+    import torch
+    st = getattr(f_grad_shared, 'state', None) or {}
+    z = numpy.load(path)
+    for k, v in st.items():
+        if k not in z.files:
+            warnings.warn('%s is not in the optimizer archive' % k)
+            continue
+        if hasattr(v, 'copy_'):
+            v.copy_(torch.from_numpy(z[k]))
+        else:
+            v[...] = z[k]
+
+
 def train(dim_word=100, dim=1000, dim_att=100, encoder='gru', decoder='gru_cond', patience=10, max_epochs=5000,
           finish_after=10000000, dispFreq=100, decay_c=0., clip_c=-1., lrate=0.01, n_words=100000, maxlen=100,
           optimizer='adadelta', batch_size=16, valid_batch_size=16, saveto='model.npz', validFreq=1000,
           saveFreq=1000, sampleFreq=100, datasets=[], valid_datasets=[], dictionary='', use_dropout=False,
-          reload_=False, verbose=False, bucket_batches=0):
+          reload_=False, verbose=False, bucket_batches=0, save_optimizer_state=False, prefetch=2):
     """Same keyword surface, side effects (npz + options pickle, log lines) and return value as the reference's
-    train() (nats.py:1230-1539).  `bucket_batches` (ours, default 0 = file order as the reference) lets the training
-    iterator sort that many batches by source length before cutting them (data_iterator.TextIterator)."""
+    train() (nats.py:1230-1539).  Ours, all defaulting to the reference behaviour:
+      bucket_batches        k > 0: the training iterator sorts k batches by source length before cutting them;
+      save_optimizer_state  also write / reload `<saveto>.opt.npz` (the reference loses the accumulators, nats.py:1433);
+      prefetch              batches prepared ahead by a background thread (0 = inline as the reference).
+    Under torchrun (one process per GPU, NCCL) every rank reads the same files; each global batch is sharded over the
+    ranks, gradients are all-reduced once per update, rank 0 alone saves / samples / logs."""
     logging.basicConfig(level=logging.DEBUG, format="%(asctime)s: %(name)s: %(levelname)s: %(message)s")
     model_options = locals().copy()
+    for _k in ('save_optimizer_state', 'prefetch'):      # not part of the reference's option pickle
+        model_options.pop(_k)
+    rank, world = parallel.world()
+    is_main = rank == 0
 
     worddicts = _load_pickle(dictionary)
     worddicts_r = dict((vv, kk) for kk, vv in worddicts.items())
@@ -1079,6 +1297,12 @@ def train(dim_word=100, dim=1000, dim_att=100, encoder='gru', decoder='gru_cond'
     print('Building optimizers...', end=' ')
     f_grad_shared, f_update = _OPTIMIZERS[optimizer](lr, tparams, grads, inps, cost)
     print('Done')
+    opt_path = '%s.opt.npz' % saveto
+    if save_optimizer_state and reload_ and os.path.exists(opt_path):
+        print('Reload optimizer state')
+        load_optimizer_state(opt_path, f_grad_shared)
+    # one workspace for the largest batch this run can produce: no regrowth (= no graph re-capture) later
+    grads.reserve(maxlen + 1, maxlen + 1, max(1, (batch_size + world - 1) // world))
     print('Optimization')
 
     history_errs = []
@@ -1095,22 +1319,33 @@ def train(dim_word=100, dim=1000, dim_att=100, encoder='gru', decoder='gru_cond'
         saveFreq = per_epoch if saveFreq == -1 else saveFreq
         sampleFreq = per_epoch if sampleFreq == -1 else sampleFreq
 
+    def _prepared(it):
+        """global batch -> this rank's shard -> padded arrays (host work a background thread can do ahead of time)"""
+        for bx, by in it:
+            n_global = len(bx)
+            if world > 1:
+                bx, by, n_global = parallel.shard_batch(bx, by, rank, world)
+            if len(bx) == 0:
+                yield None, None, None, None, n_global, 0
+                continue
+            x_, xm_, y_, ym_ = prepare_data(bx, by, maxlen=maxlen, n_words=n_words)
+            yield x_, xm_, y_, ym_, n_global, len(bx)
+
     uidx = 0
     estop = False
     for eidx in range(max_epochs):
         n_samples = 0
-        for x, y in train_it:
-            n_samples += len(x)
+        for x, x_mask, y, y_mask, n_global, n_local in _prefetched(_prepared(train_it), prefetch):
+            n_samples += n_global
             uidx += 1
             use_noise.set_value(1.)
-            x, x_mask, y, y_mask = prepare_data(x, y, maxlen=maxlen, n_words=n_words)
-            if x is None:
+            if x is None and world == 1:
                 print('Minibatch with zero sample under length ', maxlen)
                 uidx -= 1
                 continue
 
             ud_start = time.time()
-            cost_v = f_grad_shared(x, x_mask, y, y_mask)
+            cost_v = f_grad_shared(x, x_mask, y, y_mask, global_batch=n_global)
             if verbose and clip_c > 0.:
                 norm_g = float(numpy.sqrt(grads.stats[0].item()))
             f_update(lrate)
@@ -1120,20 +1355,22 @@ def train(dim_word=100, dim=1000, dim_att=100, encoder='gru', decoder='gru_cond'
                 print('NaN detected')
                 return 1., 1., 1.
 
-            if numpy.mod(uidx, dispFreq) == 0:
+            if numpy.mod(uidx, dispFreq) == 0 and is_main:
                 logger.debug('Epoch {0} Update {1} Cost {2} UD {3}'.format(eidx, uidx, cost_v, ud))
                 if verbose and clip_c > 0.:
                     logger.debug('Grad {0}'.format(norm_g))
 
-            if numpy.mod(uidx, saveFreq) == 0:
+            if numpy.mod(uidx, saveFreq) == 0 and is_main:
                 print('Saving...', end=' ')
                 params = best_p if best_p is not None else unzip(tparams)
                 numpy.savez(saveto, history_errs=history_errs, **params)
                 with open('%s.pkl' % saveto, 'wb') as f:
                     pkl.dump(model_options, f, protocol=2)
+                if save_optimizer_state:
+                    save_optimizer_state_file(opt_path, f_grad_shared)
                 print('Done')
 
-            if numpy.mod(uidx, sampleFreq) == 0:
+            if numpy.mod(uidx, sampleFreq) == 0 and is_main and x is not None:
                 for jj in range(int(numpy.minimum(5, x.shape[1]))):
                     sample, score, dec_alphas = gen_sample(tparams, f_init, f_next, x[:, jj][:, None], model_options,
                                                            trng=trng, k=1, maxlen=30, stochastic=True, argmax=False)
@@ -1180,7 +1417,10 @@ def train(dim_word=100, dim=1000, dim_att=100, encoder='gru', decoder='gru_cond'
     print('Valid ', valid_err)
 
     params = copy.copy(best_p) if best_p is not None else unzip(tparams)
-    numpy.savez(saveto, zipped_params=best_p, history_errs=history_errs, **params)
+    if is_main:
+        numpy.savez(saveto, zipped_params=best_p, history_errs=history_errs, **params)
+        if save_optimizer_state:
+            save_optimizer_state_file(opt_path, f_grad_shared)
     logger.debug('Done')
     return valid_err
 

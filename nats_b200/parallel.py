@@ -25,9 +25,21 @@ def shard(seqs_x, seqs_y, rank, world_size):
     return seqs_x[lo:hi], seqs_y[lo:hi]
 
 
-def allreduce_flat(flat):
-    """in-place SUM of the flat gradient buffer (+ cost tail) over all ranks; no-op for a single process"""
+def allreduce_flat(flat, async_op=False):
+    """in-place SUM of (a slice of) the flat gradient buffer over all ranks; no-op for a single process.
+    async_op: returns the work handle (wait() orders the current stream after the collective)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    return flat
+        w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        return w if async_op else flat
+    return None if async_op else flat
+
+
+def shard_batch(seqs_x, seqs_y, rank, world_size):
+    """What one rank trains on out of a GLOBAL batch read by every rank (train() of nats.py:1384-1411, made data
+    parallel): contiguous shards of the pairs; prepare_data cuts long pairs instead of dropping them (nats.py:210-223), so
+    the divisor of the mean cost (nats.py:1323) is the number of pairs of the global batch, known to every rank.
+    Returns (x_shard, y_shard, n_global); a shard may be empty (then that rank only contributes zeros)."""
+    n = len(seqs_x)
+    sx, sy = shard(seqs_x, seqs_y, rank, world_size)
+    return sx, sy, n
