@@ -447,10 +447,10 @@ def main():
         return 0
 
     os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep NCCL's banner off the one-JSON-line stdout
-    if world > 1:
-        # the larger gradient slice is all-reduced UNDER the persistent encoder-backward kernel, which leaves 4 SMs free:
-        # NCCL must not ask for more CTAs than that or the two kernels serialise
-        os.environ.setdefault('NCCL_MAX_NCHANNELS', os.environ.get('NATS_NCCL_CHANNELS', '4'))
+    # NCCL prints its version banner on stdout: keep stdout clean for the ONE JSON line (restored before it is printed)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     if world > 1:
         torch.cuda.set_device(local)
@@ -484,6 +484,7 @@ def main():
             c = cpu_beam_steps(w, steps=6)
             line['cpu_baseline'] = {'value': c['value'], 'unit': 'tokens/s', 'cores': c['cores'], 'kind': 'port',
                                     'sample': c['sample'], 'ms_per_step': c['ms_per_step'], 'f_init_ms': c['f_init_ms']}
+        sys.stdout.flush(); os.dup2(saved_stdout, 1)
         print(json.dumps(line))
         return 0
 
@@ -553,7 +554,7 @@ def main():
             plan.graph_fb.replay()
             graph._side.wait_stream(main_stream)
             with torch.cuda.stream(graph._side):
-                w1 = torch.distributed.all_reduce(graph.grads[graph.split:], async_op=True)
+                w1 = torch.distributed.all_reduce(graph.grads[graph.split:], async_op=True, group=graph._pg_side)
             plan.graph_fb2.replay()
             torch.distributed.all_reduce(graph.grads[:graph.split])
             w1.wait()
@@ -648,7 +649,9 @@ def main():
             c3 = cpu_beam_steps(WORKLOADS['c5'], steps=5)
             r3['cpu_baseline'] = {'value': c3['value'], 'unit': 'tokens/s', 'cores': c3['cores'], 'kind': 'port', 'sample': c3['sample'],
                                   'ms_per_step': c3['ms_per_step'], 'f_init_ms': c3['f_init_ms']}
+    sys.stdout.flush(); os.dup2(saved_stdout, 1)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0

@@ -192,6 +192,30 @@ int nats_beam_topk(nats_ctx_t* ctx, void* stream, const float* probs /* [n, n_wo
 int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, float* dst, const float* cur,
                              const int32_t* parent, int n_new, int len_cap, int hist_len, int dim);
 
+/* Device-resident bookkeeping of one beam step (replaces the host loop of nats.py:1001-1066): called after
+ * nats_sampler_next ran on k rows (rows >= live_k are ignored), nats_beam_topk with K = k, and -- for step > 0 with a
+ * distraction factor on -- nats_beam_distraction_scores with live_k = k.
+ *   nats_beam_select : candidate costs hyp_score - log p (nats.py:976), re-ranking with the penalties pen [3,k] or NULL
+ *     (:997-999, stored cost un-penalised :1004), the k - dead_k best in flattened-argsort order, then in rank order:
+ *     word 0 retires the hypothesis into out_tokens / out_len / out_score (:1037-1041), any other word makes the next
+ *     live row.  counters (device int32[4]) = {live_k, dead_k, done, finished}; scores [2,k] and tokens [2,k,maxlen] are
+ *     ping-pong buffers indexed by step parity; parents [k] (-1 = row unused), next_w [k] (input y of the next step),
+ *     fin_parent [k] (parents of the hypotheses retired in this step, compacted, -1 padded) are outputs.
+ *   nats_beam_advance: state / acc_ctx / acc_alpha rows of the next step <- outputs of nats_sampler_next gathered by
+ *     parents (:1015-1023); histories (alpha always, ctx / state when hist_ctx_src != NULL) <- history of the parent + the
+ *     current vectors; out_alpha [k,len_cap,Tx] receives the attention history of the hypotheses retired in this step.
+ * The host reads `done` (asynchronously) to stop early and copies the result buffers once at the end. */
+int nats_beam_select(nats_ctx_t* ctx, void* stream, const float* top_p, const int32_t* top_i, const float* pen,
+                     int k, int maxlen, int step, int32_t* counters, float* scores, int32_t* tokens, int32_t* parents,
+                     int64_t* next_w, int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent);
+int nats_beam_advance(nats_ctx_t* ctx, void* stream, const int32_t* parents, const int32_t* fin_parent,
+                      const int32_t* counters, int k, int len_cap, int step, int Tx, int C, int D,
+                      const float* state_o, float* state_n, const float* acc_ctx_o, float* acc_ctx_n,
+                      const float* acc_alpha_o, float* acc_alpha_n,
+                      const float* cur_alpha, const float* cur_ctx, const float* cur_state,
+                      const float* hist_alpha_src, float* hist_alpha_dst, const float* hist_ctx_src, float* hist_ctx_dst,
+                      const float* hist_state_src, float* hist_state_dst, float* out_alpha);
+
 /* ---------------------------------------------------------------- diagnostics ------------------- */
 /* The library's internal GEMM engine, exposed for the parity tests: C = op(A).op(B) (+bias) (+C), row-major,
  * path 0 = exact-fp32 FFMA kernels, path 1 = tcgen05 3xTF32 kernel with software loaders, path 2 = tcgen05 3xTF32

@@ -501,4 +501,30 @@ int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, fl
                                dim);
 }
 
+int nats_beam_select(nats_ctx_t* ctx, void* stream, const float* top_p, const int32_t* top_i, const float* pen, int k,
+                     int maxlen, int step, int32_t* counters, float* scores, int32_t* tokens, int32_t* parents,
+                     int64_t* next_w, int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent) {
+    (void)ctx;
+    NATS_REQUIRE(top_p && top_i && counters && scores && tokens && parents && next_w && out_tokens && out_len && out_score &&
+                     fin_parent, "null argument");
+    return beam_select(reinterpret_cast<cudaStream_t>(stream), top_p, top_i, pen, k, maxlen, step, counters, scores, tokens,
+                       parents, reinterpret_cast<long long*>(next_w), out_tokens, out_len, out_score, fin_parent);
+}
+
+int nats_beam_advance(nats_ctx_t* ctx, void* stream, const int32_t* parents, const int32_t* fin_parent,
+                      const int32_t* counters, int k, int len_cap, int step, int Tx, int C, int D, const float* state_o,
+                      float* state_n, const float* acc_ctx_o, float* acc_ctx_n, const float* acc_alpha_o, float* acc_alpha_n,
+                      const float* cur_alpha, const float* cur_ctx, const float* cur_state, const float* hist_alpha_src,
+                      float* hist_alpha_dst, const float* hist_ctx_src, float* hist_ctx_dst, const float* hist_state_src,
+                      float* hist_state_dst, float* out_alpha) {
+    (void)ctx;
+    NATS_REQUIRE(parents && fin_parent && counters && state_o && state_n && acc_ctx_o && acc_ctx_n && acc_alpha_o &&
+                     acc_alpha_n && cur_alpha && hist_alpha_src && hist_alpha_dst && out_alpha, "null argument");
+    NATS_REQUIRE(hist_ctx_src == nullptr || (hist_ctx_dst && hist_state_src && hist_state_dst && cur_ctx && cur_state),
+                 "context / state histories come together");
+    return beam_advance(reinterpret_cast<cudaStream_t>(stream), parents, fin_parent, counters, k, len_cap, step, Tx, C, D,
+                        state_o, state_n, acc_ctx_o, acc_ctx_n, acc_alpha_o, acc_alpha_n, cur_alpha, cur_ctx, cur_state,
+                        hist_alpha_src, hist_alpha_dst, hist_ctx_src, hist_ctx_dst, hist_state_src, hist_state_dst, out_alpha);
+}
+
 }  // extern "C"

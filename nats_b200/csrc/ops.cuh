@@ -179,5 +179,14 @@ int beam_distraction_scores(cudaStream_t st, const float* hist_alpha, const floa
 int beam_topk(cudaStream_t st, const float* probs, int n, int V, int K, int mask_unk, float* out_p, int32_t* out_idx);
 int beam_reorder_append(cudaStream_t st, const float* src, float* dst, const float* cur, const int32_t* parent,
                         int n_new, int len_cap, int hist_len, int dim);
+// device-resident bookkeeping of one beam step (nats.py:976-1066): see ops_beam.cu
+int beam_select(cudaStream_t st, const float* top_p, const int32_t* top_i, const float* pen, int k, int maxlen, int step,
+                int32_t* counters, float* scores, int32_t* tokens, int32_t* parents, long long* next_w,
+                int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent);
+int beam_advance(cudaStream_t st, const int32_t* parents, const int32_t* fin_parent, const int32_t* counters, int k,
+                 int len_cap, int step, int Tx, int C, int D, const float* state_o, float* state_n, const float* acc_ctx_o,
+                 float* acc_ctx_n, const float* acc_alpha_o, float* acc_alpha_n, const float* cur_alpha, const float* cur_ctx,
+                 const float* cur_state, const float* hist_alpha_src, float* hist_alpha_dst, const float* hist_ctx_src,
+                 float* hist_ctx_dst, const float* hist_state_src, float* hist_state_dst, float* out_alpha);
 
 }  // namespace nats

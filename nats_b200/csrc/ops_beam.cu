@@ -69,6 +69,7 @@ __global__ void beam_reorder_kernel(const float* __restrict__ src, float* __rest
                                     int hist_len, int dim) {
     const int j = blockIdx.x, s = blockIdx.y;
     const int par = parent[j];
+    if (par < 0) return;                                              // row not alive after this step
     const float* from = (s < hist_len) ? src + ((long long)par * len_cap + s) * dim : cur + (long long)par * dim;
     float* to = dst + ((long long)j * len_cap + s) * dim;
     for (int t = threadIdx.x; t < dim; t += blockDim.x) to[t] = from[t];
@@ -101,6 +102,163 @@ int beam_reorder_append(cudaStream_t st, const float* src, float* dst, const flo
     return 0;
 }
 
+
+namespace {
+
+constexpr int kMaxBeam = 32;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident beam bookkeeping (nats.py:976-1066), ONE warp: candidate costs from the per-row top-k, distraction
+// re-ranking (nats.py:997-999; the stored cost stays un-penalised, :1004), selection of the k - dead_k best in the
+// stable order of a flattened argsort, then the reference's loop over the selected candidates in rank order: a
+// candidate ending in word 0 retires into the result slots (:1037-1041), the others become the live rows of the next step.
+//   counters[0] live_k, [1] dead_k, [2] done flag (set when live_k < 1 or dead_k >= k, :1057), [3] finished so far
+//   scores / tokens are ping-pong buffers selected by the step parity; tokens rows hold `step` words on entry
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) beam_select_kernel(const float* __restrict__ top_p, const int32_t* __restrict__ top_i,
+                                                         const float* __restrict__ pen, int k, int maxlen, int step,
+                                                         int32_t* __restrict__ counters, float* __restrict__ scores,
+                                                         int32_t* __restrict__ tokens, int32_t* __restrict__ parents,
+                                                         long long* __restrict__ next_w, int32_t* __restrict__ out_tokens,
+                                                         int32_t* __restrict__ out_len, float* __restrict__ out_score,
+                                                         int32_t* __restrict__ fin_parent) {
+    __shared__ float s_rank[kMaxBeam * kMaxBeam];
+    __shared__ float s_cost[kMaxBeam * kMaxBeam];
+    __shared__ int s_sel[kMaxBeam];
+    const int lane = threadIdx.x;
+    const int cur = step & 1, nxt = cur ^ 1;
+    const float* sc_in = scores + cur * k;
+    float* sc_out = scores + nxt * k;
+    const int32_t* tk_in = tokens + (long long)cur * k * maxlen;
+    int32_t* tk_out = tokens + (long long)nxt * k * maxlen;
+    for (int j = lane; j < k; j += 32) { parents[j] = -1; fin_parent[j] = -1; }
+    const int live_k = counters[0], dead_k = counters[1];
+    if (counters[2] != 0) return;                                     // finished earlier: nothing moves any more
+    const int n_keep = k - dead_k;
+    const int ncand = live_k * k;
+    for (int e = lane; e < k * k; e += 32) {
+        float cost = INFINITY, rank = INFINITY;
+        if (e < ncand) {
+            const int r = e / k;
+            if (top_i[e] >= 0) {
+                cost = sc_in[r] - logf(top_p[e]);                     // nats.py:976
+                rank = cost;
+                if (pen != nullptr && step > 0) rank = cost + pen[r] + pen[k + r] + pen[2 * k + r];     // :997
+            }
+        }
+        s_cost[e] = cost;
+        s_rank[e] = rank;
+    }
+    __syncwarp();
+    // n_keep rounds of (value, index) argmin: the order of a stable argsort over the flattened [live_k, k] array
+    int nsel = 0;
+    for (int r = 0; r < n_keep; ++r) {
+        float bv = INFINITY;
+        int bi = 0x7fffffff;
+        for (int e = lane; e < ncand; e += 32) {
+            const float v = s_rank[e];
+            if (v < bv || (v == bv && e < bi)) { bv = v; bi = e; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (bi == 0x7fffffff || top_i[bi] < 0) break;                 // fewer valid candidates than n_keep
+        if (lane == 0) { s_sel[r] = bi; s_rank[bi] = __int_as_float(0x7fc00000); }      // consumed: NaN never compares smaller or equal
+        nsel = r + 1;
+        __syncwarp();
+    }
+    int new_live = 0, nfin = counters[3], ndead = dead_k, fin_now = 0;
+    for (int r = 0; r < nsel; ++r) {                                  // rank order, as the reference's zip loop (:1010-1052)
+        const int e = s_sel[r];
+        const int ti = e / k, wi = top_i[e];
+        const float ci = s_cost[e];
+        if (wi == 0) {
+            int32_t* dst = out_tokens + (long long)nfin * maxlen;
+            for (int t = lane; t < step; t += 32) dst[t] = tk_in[(long long)ti * maxlen + t];
+            if (lane == 0) { dst[step] = 0; out_len[nfin] = step + 1; out_score[nfin] = ci; fin_parent[fin_now] = ti; }
+            ++nfin; ++ndead; ++fin_now;
+        } else {
+            int32_t* dst = tk_out + (long long)new_live * maxlen;
+            for (int t = lane; t < step; t += 32) dst[t] = tk_in[(long long)ti * maxlen + t];
+            if (lane == 0) { dst[step] = wi; sc_out[new_live] = ci; parents[new_live] = ti; next_w[new_live] = wi; }
+            ++new_live;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        counters[0] = new_live; counters[1] = ndead; counters[3] = nfin;
+        if (new_live < 1 || ndead >= k) counters[2] = 1;
+    }
+}
+
+// rows of the next step <- rows of their parents: dst[j,:] = src[parent[j],:] for the three state buffers of f_next
+__global__ void __launch_bounds__(256) beam_gather_kernel(const int32_t* __restrict__ parent, const float* __restrict__ s0,
+                                                          float* __restrict__ d0, int n0, const float* __restrict__ s1,
+                                                          float* __restrict__ d1, int n1, const float* __restrict__ s2,
+                                                          float* __restrict__ d2, int n2) {
+    const int j = blockIdx.x, par = parent[j];
+    if (par < 0) return;
+    const float* src = blockIdx.y == 0 ? s0 : (blockIdx.y == 1 ? s1 : s2);
+    float* dst = blockIdx.y == 0 ? d0 : (blockIdx.y == 1 ? d1 : d2);
+    const int n = blockIdx.y == 0 ? n0 : (blockIdx.y == 1 ? n1 : n2);
+    for (int t = threadIdx.x; t < n; t += 256) dst[(long long)j * n + t] = src[(long long)par * n + t];
+}
+
+// attention history of the hypotheses that retired in this step (nats.py:1040): out[f] = history(parent) + current alpha
+__global__ void __launch_bounds__(256) beam_finish_alpha_kernel(const int32_t* __restrict__ fin_parent,
+                                                                const int32_t* __restrict__ counters,
+                                                                const float* __restrict__ hist, const float* __restrict__ cur,
+                                                                float* __restrict__ out, int len_cap, int step, int Tx) {
+    const int f = blockIdx.x, s = blockIdx.y;
+    const int par = fin_parent[f];
+    if (par < 0) return;
+    int nf_before = counters[3];
+    for (int q = 0; q < gridDim.x; ++q)                               // slots are assigned in order: count this step's retirements
+        if (fin_parent[q] >= 0) --nf_before;
+    const float* from = (s < step) ? hist + ((long long)par * len_cap + s) * Tx : cur + (long long)par * Tx;
+    float* to = out + ((long long)(nf_before + f) * len_cap + s) * Tx;
+    for (int t = threadIdx.x; t < Tx; t += 256) to[t] = from[t];
+}
+
+}  // namespace
+
+int beam_select(cudaStream_t st, const float* top_p, const int32_t* top_i, const float* pen, int k, int maxlen, int step,
+                int32_t* counters, float* scores, int32_t* tokens, int32_t* parents, long long* next_w,
+                int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent) {
+    NATS_REQUIRE(k >= 1 && k <= kMaxBeam && step >= 0 && step < maxlen, "beam_select shape (beam <= 32)");
+    ProfScope ps(st, K_BEAM);
+    beam_select_kernel<<<1, 32, 0, st>>>(top_p, top_i, pen, k, maxlen, step, counters, scores, tokens, parents, next_w,
+                                         out_tokens, out_len, out_score, fin_parent);
+    NATS_LAUNCH_OK();
+    return 0;
+}
+
+int beam_advance(cudaStream_t st, const int32_t* parents, const int32_t* fin_parent, const int32_t* counters, int k,
+                 int len_cap, int step, int Tx, int C, int D, const float* state_o, float* state_n, const float* acc_ctx_o,
+                 float* acc_ctx_n, const float* acc_alpha_o, float* acc_alpha_n, const float* cur_alpha, const float* cur_ctx,
+                 const float* cur_state, const float* hist_alpha_src, float* hist_alpha_dst, const float* hist_ctx_src,
+                 float* hist_ctx_dst, const float* hist_state_src, float* hist_state_dst, float* out_alpha) {
+    NATS_REQUIRE(k >= 1 && step >= 0 && step < len_cap, "beam_advance shape");
+    ProfScope ps(st, K_BEAM);
+    beam_gather_kernel<<<dim3(k, 3), 256, 0, st>>>(parents, state_o, state_n, D, acc_ctx_o, acc_ctx_n, C, acc_alpha_o,
+                                                   acc_alpha_n, Tx);
+    NATS_LAUNCH_OK();
+    beam_finish_alpha_kernel<<<dim3(k, step + 1), 256, 0, st>>>(fin_parent, counters, hist_alpha_src, cur_alpha, out_alpha,
+                                                                len_cap, step, Tx);
+    NATS_LAUNCH_OK();
+    beam_reorder_kernel<<<dim3(k, step + 1), 256, 0, st>>>(hist_alpha_src, hist_alpha_dst, cur_alpha, parents, len_cap, step, Tx);
+    NATS_LAUNCH_OK();
+    if (hist_ctx_src != nullptr) {
+        beam_reorder_kernel<<<dim3(k, step + 1), 256, 0, st>>>(hist_ctx_src, hist_ctx_dst, cur_ctx, parents, len_cap, step, C);
+        NATS_LAUNCH_OK();
+        beam_reorder_kernel<<<dim3(k, step + 1), 256, 0, st>>>(hist_state_src, hist_state_dst, cur_state, parents, len_cap, step, D);
+        NATS_LAUNCH_OK();
+    }
+    return 0;
+}
 
 namespace {
 

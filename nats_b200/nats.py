@@ -466,6 +466,8 @@ class ModelGraph(object):
         self.rank, self.world = parallel.world()
         self.split = int(self.engine.lib.nats_grad_split(ctypes.byref(self.dims)))
         self._side = None
+        self._pg_side = None
+        self._pg_side_tried = False
         self._cost_ring = None
         self._cost_slot = 0
 
@@ -610,11 +612,14 @@ class ModelGraph(object):
             # only the encoder slice is reduced after it
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.engine.device)
+            if not self._pg_side_tried:                       # collective call: every rank reaches this in its first step
+                self._pg_side_tried = True
+                self._pg_side = parallel.side_group(int(os.environ.get('NATS_NCCL_SIDE_CTAS', '4')))
             main = torch.cuda.current_stream(self.engine.device)
             self._run(p, 'graph_fb', lambda: (self.enqueue_fwd(p), self.enqueue_bwd(p, scale, 1)))
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                w1 = parallel.allreduce_flat(self.grads[self.split:], async_op=True)
+                w1 = parallel.allreduce_flat(self.grads[self.split:], async_op=True, group=self._pg_side)
             self._run(p, 'graph_fb2', lambda: self.enqueue_bwd(p, scale, 2))
             parallel.allreduce_flat(self.grads[:self.split])
             if w1 is not None:

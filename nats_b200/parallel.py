@@ -25,14 +25,32 @@ def shard(seqs_x, seqs_y, rank, world_size):
     return seqs_x[lo:hi], seqs_y[lo:hi]
 
 
-def allreduce_flat(flat, async_op=False):
+def allreduce_flat(flat, async_op=False, group=None):
     """in-place SUM of (a slice of) the flat gradient buffer over all ranks; no-op for a single process.
     async_op: returns the work handle (wait() orders the current stream after the collective)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op, group=group)
         return w if async_op else flat
     return None if async_op else flat
+
+
+def side_group(max_ctas=4):
+    """A second NCCL communicator limited to `max_ctas` CTAs, for the all-reduce that runs UNDER the persistent encoder-
+    backward kernel: that kernel holds 144 of the 148 SMs for ~3 ms, a collective asking for more CTAs than the SMs left
+    would simply wait for it to finish.  None when not applicable (single process, gloo, old torch)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    if dist.get_backend() != 'nccl':
+        return None
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(max_ctas)
+        opts.config.min_ctas = 1
+        return dist.new_group(backend='nccl', pg_options=opts)
+    except Exception:
+        return None
 
 
 def shard_batch(seqs_x, seqs_y, rank, world_size):
