@@ -198,7 +198,7 @@ int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, fl
  *   nats_beam_select : candidate costs hyp_score - log p (nats.py:976), re-ranking with the penalties pen [3,k] or NULL
  *     (:997-999, stored cost un-penalised :1004), the k - dead_k best in flattened-argsort order, then in rank order:
  *     word 0 retires the hypothesis into out_tokens / out_len / out_score (:1037-1041), any other word makes the next
- *     live row.  counters (device int32[4]) = {live_k, dead_k, done, finished}; scores [2,k] and tokens [2,k,maxlen] are
+ *     live row.  counters (device int32[8]) = {live_k, dead_k, done, finished, last effective step, -, -, -}; scores [2,k] and tokens [2,k,maxlen] are
  *     ping-pong buffers indexed by step parity; parents [k] (-1 = row unused), next_w [k] (input y of the next step),
  *     fin_parent [k] (parents of the hypotheses retired in this step, compacted, -1 padded) are outputs.
  *   nats_beam_advance: state / acc_ctx / acc_alpha rows of the next step <- outputs of nats_sampler_next gathered by

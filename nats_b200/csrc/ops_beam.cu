@@ -112,7 +112,8 @@ constexpr int kMaxBeam = 32;
 // re-ranking (nats.py:997-999; the stored cost stays un-penalised, :1004), selection of the k - dead_k best in the
 // stable order of a flattened argsort, then the reference's loop over the selected candidates in rank order: a
 // candidate ending in word 0 retires into the result slots (:1037-1041), the others become the live rows of the next step.
-//   counters[0] live_k, [1] dead_k, [2] done flag (set when live_k < 1 or dead_k >= k, :1057), [3] finished so far
+//   counters[0] live_k, [1] dead_k, [2] done flag (set when live_k < 1 or dead_k >= k, :1057), [3] finished so far,
+//   [4] index of the last step that was carried out (steps issued after `done` change nothing)
 //   scores / tokens are ping-pong buffers selected by the step parity; tokens rows hold `step` words on entry
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) beam_select_kernel(const float* __restrict__ top_p, const int32_t* __restrict__ top_i,
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const float* __restrict
     }
     __syncwarp();
     if (lane == 0) {
-        counters[0] = new_live; counters[1] = ndead; counters[3] = nfin;
+        counters[0] = new_live; counters[1] = ndead; counters[3] = nfin; counters[4] = step;
         if (new_live < 1 || ndead >= k) counters[2] = 1;
     }
 }

@@ -959,9 +959,21 @@ def build_sampler(tparams, options, trng=None):
         eng.launches += 1
         return tp.cpu().numpy(), ti.cpu().numpy()
 
+    def next_device(y_d, ctx_d, pctx_d, st_d, ac_d, aa_d, Tx, n, outs):
+        """f_next entirely on device tensors (rows of ONE source: zero batch stride), outputs into preallocated `outs`"""
+        ws, nbytes = ws_for(Tx, n)
+        _lib.check(eng.lib.nats_sampler_next(
+            eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(y_d), _ptr(ctx_d), C, 0, _ptr(pctx_d), A, 0,
+            _ptr(st_d), _ptr(ac_d), _ptr(aa_d), Tx, n, seed, counter[0], _ptr(ws), nbytes, _ptr(outs[0]), _ptr(outs[1]),
+            _ptr(outs[2]), _ptr(outs[3]), _ptr(outs[4]), _ptr(outs[5]), _ptr(outs[6])), 'nats_sampler_next')
+        eng.launches += 1
+        counter[0] += 1
+
     f_next.last_device = None
     f_next.engine = eng
     f_next.topk = topk
+    f_next.next_device = next_device
+    f_next.dims = (V, W, D, A)
     return f_init, f_next
 
 
@@ -1026,6 +1038,104 @@ def _tile_ctx(ctx0, live_k):
     return numpy.tile(ctx0, [live_k, 1])
 
 
+def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_factor, state_factor, _trace):
+    """Beam search with every piece of bookkeeping on the device (replaces the host loop of
+    nats.py:1001-1066): per step ONE f_next on k rows (rows >= live_k are ignored), the distraction penalties, a per-row
+    top-k, nats_beam_select (candidate merge, re-ranking, EOS retirement) and nats_beam_advance (state / accumulator /
+    history gathers).  The host reads one 4-byte `done` flag per step, one step late (the GPU queue never drains), and
+    copies tokens, scores and attention histories back once at the end.  Returns the reference's three lists."""
+    eng = f_next.engine
+    torch = eng.torch
+    lib = eng.lib
+    V, W, D, A = f_next.dims
+    C = 2 * D
+    init_state, ctx0 = f_init(x)
+    handle = getattr(ctx0, '_nats_handle', None)
+    ctx_d, pctx_d = handle.ctx_dev, handle.pctx_dev
+    Tx = int(ctx0.shape[0])
+    dev = eng.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    distract = kl_factor > 0. or ctx_factor > 0. or state_factor > 0.
+    # state of the live rows (ping-pong), f_next outputs, histories, results
+    state = [torch.zeros((k, D), **f32) for _ in range(2)]
+    acc_ctx = [torch.zeros((k, C), **f32) for _ in range(2)]
+    acc_alpha = [torch.zeros((k, Tx), **f32) for _ in range(2)]
+    state[0][0].copy_(torch.from_numpy(numpy.ascontiguousarray(init_state, dtype='float32')).reshape(-1)[:D])
+    outs = [torch.empty((k, V), **f32), torch.empty((k,), dtype=torch.int64, device=dev), torch.empty((k, D), **f32),
+            torch.empty((k, Tx), **f32), torch.empty((k, C), **f32), torch.empty((k, C), **f32), torch.empty((k, Tx), **f32)]
+    hist_alpha = [torch.zeros((k, maxlen, Tx), **f32) for _ in range(2)]
+    hist_ctx = [torch.zeros((k, maxlen, C), **f32) for _ in range(2)] if distract else [None, None]
+    hist_state = [torch.zeros((k, maxlen, D), **f32) for _ in range(2)] if distract else [None, None]
+    out_alpha = torch.zeros((k, maxlen, Tx), **f32)
+    counters = torch.tensor([1, 0, 0, 0, -1, 0, 0, 0], **i32)          # live_k, dead_k, done, finished, last effective step
+    scores = torch.zeros((2, k), **f32)
+    tokens = torch.zeros((2, k, maxlen), **i32)
+    parents = torch.zeros((k,), **i32)
+    fin_parent = torch.zeros((k,), **i32)
+    next_w = torch.full((k,), -1, dtype=torch.int64, device=dev)          # BOS marker -> zero embedding
+    out_tokens = torch.zeros((k, maxlen), **i32)
+    out_len = torch.zeros((k,), **i32)
+    out_score = torch.zeros((k,), **f32)
+    top_p, top_i = torch.empty((k, k), **f32), torch.empty((k, k), **i32)
+    pen = torch.zeros((3 * k,), **f32)
+    scratch = torch.zeros((3 * k * maxlen + 16,), **f32)
+    flags = [(torch.zeros(8, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+    for ii in range(maxlen):
+        cur = ii & 1
+        f_next.next_device(next_w, ctx_d, pctx_d, state[cur], acc_ctx[cur], acc_alpha[cur], Tx, k, outs)
+        use_pen = distract and ii > 0
+        if use_pen:
+            _lib.check(lib.nats_beam_distraction_scores(
+                eng.ctx, eng.stream(), _ptr(hist_alpha[cur]), _ptr(hist_ctx[cur]), _ptr(hist_state[cur]), maxlen, ii, k, Tx, C, D,
+                _ptr(outs[3]), _ptr(outs[4]), _ptr(outs[2]), ctypes.c_float(kl_factor), ctypes.c_float(ctx_factor),
+                ctypes.c_float(state_factor), _ptr(scratch), _ptr(pen)), 'nats_beam_distraction_scores')
+            if _trace is not None:
+                live_now = int(counters[0].item())
+                _trace.append(dict(ii=ii, pen=pen.cpu().numpy().reshape(3, k)[:, :live_now].copy()))
+        _lib.check(lib.nats_beam_topk(eng.ctx, eng.stream(), _ptr(outs[0]), k, V, k, 0 if use_unk else 1, _ptr(top_p),
+                                      _ptr(top_i)), 'nats_beam_topk')
+        _lib.check(lib.nats_beam_select(eng.ctx, eng.stream(), _ptr(top_p), _ptr(top_i), _ptr(pen) if use_pen else None, k, maxlen,
+                                        ii, _ptr(counters), _ptr(scores), _ptr(tokens), _ptr(parents), _ptr(next_w),
+                                        _ptr(out_tokens), _ptr(out_len), _ptr(out_score), _ptr(fin_parent)), 'nats_beam_select')
+        _lib.check(lib.nats_beam_advance(
+            eng.ctx, eng.stream(), _ptr(parents), _ptr(fin_parent), _ptr(counters), k, maxlen, ii, Tx, C, D,
+            _ptr(outs[2]), _ptr(state[cur ^ 1]), _ptr(outs[5]), _ptr(acc_ctx[cur ^ 1]), _ptr(outs[6]), _ptr(acc_alpha[cur ^ 1]),
+            _ptr(outs[3]), _ptr(outs[4]), _ptr(outs[2]), _ptr(hist_alpha[cur]), _ptr(hist_alpha[cur ^ 1]),
+            _ptr(hist_ctx[cur]), _ptr(hist_ctx[cur ^ 1]), _ptr(hist_state[cur]), _ptr(hist_state[cur ^ 1]), _ptr(out_alpha)),
+            'nats_beam_advance')
+        eng.launches += 4
+        buf, ev = flags[cur]
+        buf.copy_(counters, non_blocking=True)
+        ev.record()
+        if ii > 0:                                            # the flag of the PREVIOUS step: its copy has long completed
+            pbuf, pev = flags[cur ^ 1]
+            pev.synchronize()
+            if int(pbuf[2]) != 0:
+                break
+    torch.cuda.synchronize(dev)
+    cnt = counters.cpu().numpy()
+    live_k, n_fin = int(cnt[0]), int(cnt[3])
+    # with the one-step-late flag a step may have run after `done`: nats_beam_select leaves everything untouched then
+    fin_tok, fin_len, fin_sc = out_tokens.cpu().numpy(), out_len.cpu().numpy(), out_score.cpu().numpy()
+    fin_al = out_alpha.cpu().numpy()
+    sample, sample_score, sample_dec_alphas = [], [], []
+    for f in range(n_fin):
+        L = int(fin_len[f])
+        sample.append([int(t) for t in fin_tok[f, :L]])
+        sample_score.append(numpy.float32(fin_sc[f]))
+        sample_dec_alphas.append([fin_al[f, t].copy() for t in range(L)])
+    if live_k > 0:                                            # dump what is still alive (nats.py:1068-1074)
+        s_last = int(cnt[4])                                  # step s wrote the rows of parity (s + 1) & 1, s + 1 words each
+        par, L = (s_last + 1) & 1, s_last + 1
+        lt, ls, ha = tokens[par].cpu().numpy(), scores[par].cpu().numpy(), hist_alpha[par].cpu().numpy()
+        for j in range(live_k):
+            sample.append([int(t) for t in lt[j, :L]])
+            sample_score.append(numpy.float32(ls[j]))
+            sample_dec_alphas.append([ha[j, t].copy() for t in range(L)])
+    return sample, sample_score, sample_dec_alphas
+
+
 def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, stochastic=True, argmax=False,
                use_unk=False, kl_factor=0, ctx_factor=0, state_factor=0, _scorer_factory=None, _trace=None):
     """Stochastic sampling or beam search with distraction re-ranking; same arguments, return values and
@@ -1033,6 +1143,10 @@ def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, s
     the three penalties only re-rank (nats.py:997-999)."""
     if k > 1:
         assert not stochastic, 'Beam search does not support stochastic sampling'
+    if (not stochastic and _scorer_factory is None and getattr(f_next, 'next_device', None) is not None and k <= 32
+            and os.environ.get('NATS_DEVICE_BEAM', '1') != '0' and numpy.ndim(x) == 2 and numpy.shape(x)[1] == 1
+            and getattr(f_init, '__module__', None) == __name__):
+        return _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_factor, state_factor, _trace)
 
     sample, sample_score, sample_dec_alphas = [], [], []
     if stochastic:
