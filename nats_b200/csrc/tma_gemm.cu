@@ -205,31 +205,47 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
             // ===================== MMA issuer =====================
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int sr = kb % NR, sl = kb % NL;
-                mbar_wait_spin(&lo_full[sl], (uint32_t)((kb / NL) & 1));     // implies tma_full[sr] (the residual warps waited on it)
-                if (tr && kb == 0) tr_s[7] = gtimer();
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
-                const uint32_t lo = smem_base + kLoBase + (uint32_t)sl * kRawStage;
-                const uint64_t a_raw = A_MN ? desc_mnmajor(raw) : desc_kmajor(raw);
-                const uint64_t a_lo = A_MN ? desc_mnmajor(lo) : desc_kmajor(lo);
-                const uint64_t b_raw = B_MN ? desc_mnmajor(raw + kABytes) : desc_kmajor(raw + kABytes);
-                const uint64_t b_lo = B_MN ? desc_mnmajor(lo + kABytes) : desc_kmajor(lo + kABytes);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint64_t adv_a = (uint64_t)((A_MN ? kk * 1024 : kk * 32) >> 4);
-                    const uint64_t adv_b = (uint64_t)((B_MN ? kk * 1024 : kk * 32) >> 4);
-                    const int gstep = kb * 4 + kk;
-                    if (grp.dbg_mode != 2) {
-                        umma_tf32(tmem_d + 3u * BN, a_lo + adv_a, b_raw + adv_b, idesc, gstep != 0 ? 1u : 0u);
-                        umma_tf32(tmem_d + 3u * BN, a_raw + adv_a, b_lo + adv_b, idesc, 1u);
-                    }
-                    umma_tf32(tmem_d + (uint32_t)(gstep % 3) * BN, a_raw + adv_a, b_raw + adv_b, idesc, gstep >= 3 ? 1u : 0u);
+            // straight-line issue code (see enc_tc.cu / the TS kernel below): first k-block peeled, accumulator of a k-step
+            // fixed by its position in the block, ring indices as running counters, descriptors advanced by constants
+            const uint64_t a_raw0 = A_MN ? desc_mnmajor(smem_base) : desc_kmajor(smem_base);
+            const uint64_t b_raw0 = B_MN ? desc_mnmajor(smem_base + kABytes) : desc_kmajor(smem_base + kABytes);
+            const uint64_t a_lo0 = A_MN ? desc_mnmajor(smem_base + kLoBase) : desc_kmajor(smem_base + kLoBase);
+            const uint64_t b_lo0 = B_MN ? desc_mnmajor(smem_base + kLoBase + kABytes) : desc_kmajor(smem_base + kLoBase + kABytes);
+            constexpr uint64_t kStageInc = (uint64_t)(kRawStage >> 4);
+            constexpr uint64_t kAdvA = (uint64_t)((A_MN ? 1024 : 32) >> 4), kAdvB = (uint64_t)((B_MN ? 1024 : 32) >> 4);
+            const uint32_t acc_x = tmem_d + 3u * BN;
+            const bool full3 = grp.dbg_mode != 2;
+            int sr = 0, sl = 0;
+            uint32_t lpar = 0;
+#define SS_STEP(KK, ACC, FIRSTMAIN, FIRSTX)                                                                              \
+    if (full3) {                                                                                                         \
+        umma_tf32(acc_x, a_lo + (KK) * kAdvA, b_raw + (KK) * kAdvB, idesc, (FIRSTX) ? 0u : 1u);                          \
+        umma_tf32(acc_x, a_raw + (KK) * kAdvA, b_lo + (KK) * kAdvB, idesc, 1u);                                          \
+    }                                                                                                                    \
+    umma_tf32(tmem_d + (uint32_t)(ACC) * BN, a_raw + (KK) * kAdvA, b_raw + (KK) * kAdvB, idesc, (FIRSTMAIN) ? 0u : 1u);
+#define SS_BLOCK(FIRST)                                                                                                  \
+    {                                                                                                                    \
+        mbar_wait_spin(&lo_full[sl], (lpar >> sl) & 1u);     /* implies tma_full[sr] (the residual warps waited on it) */  \
+        lpar ^= 1u << sl;                                                                                                \
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                                  \
+        const uint64_t a_raw = a_raw0 + (uint64_t)sr * kStageInc, b_raw = b_raw0 + (uint64_t)sr * kStageInc;             \
+        const uint64_t a_lo = a_lo0 + (uint64_t)sl * kStageInc, b_lo = b_lo0 + (uint64_t)sl * kStageInc;                 \
+        SS_STEP(0, 0, FIRST, FIRST) SS_STEP(1, 1, FIRST, false) SS_STEP(2, 2, FIRST, false) SS_STEP(3, 0, false, false)  \
+        umma_commit(&raw_empty[sr]);                         /* both slots are free once these MMAs retire */            \
+        umma_commit(&lo_empty[sl]);                                                                                      \
+    }
+            if (nkb > 0) {
+                SS_BLOCK(true)
+                if (tr) tr_s[7] = gtimer();
+                sr = 1 % NR; sl = 1 % NL;
+                for (int kb = 1; kb < nkb; ++kb) {
+                    SS_BLOCK(false)
+                    sr = (sr + 1 == NR) ? 0 : sr + 1;
+                    sl = (sl + 1 == NL) ? 0 : sl + 1;
                 }
-                umma_commit(&raw_empty[sr]);                                 // both slots are free once these MMAs retire
-                umma_commit(&lo_empty[sl]);
             }
+#undef SS_BLOCK
+#undef SS_STEP
             umma_commit(&accum_bar);
             if (tr) tr_s[8] = gtimer();
         }
@@ -531,24 +547,44 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_ts_kernel(const __grid_c
             const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((128u >> 4) << 24);
             const uint32_t idesc1 = idesc_base | ((uint32_t)(BN >> 3) << 17);            // N = BN
             const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * BN) >> 3) << 17);      // N = 2*BN: [B_raw | B_lo]
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int sr = kb % NR, sl = kb % NL;
-                mbar_wait_spin(&a_full[sl], (uint32_t)((kb / NL) & 1));
-                if (tr && kb == 0) tr_s[7] = gtimer();
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t raw = smem_base + (uint32_t)sr * kRawStage;
-                const uint64_t b_raw = B_MN ? desc_mnmajor(raw + kABytes) : desc_kmajor(raw + kABytes);   // B_lo follows contiguously
-                const uint32_t a_hi = tmem_a0 + (uint32_t)(sl * 64), a_lo = a_hi + 32;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint64_t adv_b = (uint64_t)((B_MN ? kk * 1024 : kk * 32) >> 4);
-                    const int gstep = kb * 4 + kk;
-                    umma_tf32_ts(tmem_d + NACC * 2u * BN, a_lo + 8u * kk, b_raw + adv_b, idesc1, gstep != 0 ? 1u : 0u);
-                    umma_tf32_ts(tmem_d + (uint32_t)(gstep % NACC) * 2u * BN, a_hi + 8u * kk, b_raw + adv_b, idesc2,
-                                 gstep >= (int)NACC ? 1u : 0u);
+            // Straight-line issue code (see enc_tc.cu): a single thread executes dependent scalar instructions at ~10 cycles
+            // each, so runtime accumulate predicates, modulo rotations and descriptor rebuilds between two MMAs cost more
+            // than the MMAs.  The first k-block is peeled (its MMAs overwrite the accumulators), the accumulator of a k-step
+            // is fixed by its position in the block (kk % NACC), ring indices are running counters.
+            const uint64_t b_desc0 = B_MN ? desc_mnmajor(smem_base + kABytes) : desc_kmajor(smem_base + kABytes);   // B_lo follows contiguously
+            constexpr uint64_t kStageInc = (uint64_t)(kRawStage >> 4);
+            constexpr uint64_t kAdv = (uint64_t)((B_MN ? 1024 : 32) >> 4);
+            const uint32_t acc_lo = tmem_d + NACC * 2u * BN;
+            int sr = 0, sl = 0;
+            uint32_t apar = 0;                               // parity bit per TMEM stage
+#define TS_BLOCK(FIRST)                                                                                                   \
+    {                                                                                                                     \
+        mbar_wait_spin(&a_full[sl], (apar >> sl) & 1u);                                                                   \
+        apar ^= 1u << sl;                                                                                                 \
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                                   \
+        const uint64_t b_raw = b_desc0 + (uint64_t)sr * kStageInc;                                                        \
+        const uint32_t a_hi = tmem_a0 + (uint32_t)(sl * 64), a_lo = a_hi + 32;                                            \
+        umma_tf32_ts(acc_lo, a_lo, b_raw, idesc1, (FIRST) ? 0u : 1u);                                                     \
+        umma_tf32_ts(tmem_d, a_hi, b_raw, idesc2, (FIRST) ? 0u : 1u);                                                     \
+        umma_tf32_ts(acc_lo, a_lo + 8u, b_raw + kAdv, idesc1, 1u);                                                        \
+        umma_tf32_ts(tmem_d + 2u * BN, a_hi + 8u, b_raw + kAdv, idesc2, (FIRST) ? 0u : 1u);                               \
+        umma_tf32_ts(acc_lo, a_lo + 16u, b_raw + 2 * kAdv, idesc1, 1u);                                                   \
+        umma_tf32_ts(tmem_d + (NACC > 2 ? 4u * BN : 0u), a_hi + 16u, b_raw + 2 * kAdv, idesc2, (FIRST) && NACC > 2 ? 0u : 1u); \
+        umma_tf32_ts(acc_lo, a_lo + 24u, b_raw + 3 * kAdv, idesc1, 1u);                                                   \
+        umma_tf32_ts(tmem_d + (NACC > 2 ? 0u : 2u * BN), a_hi + 24u, b_raw + 3 * kAdv, idesc2, 1u);                       \
+    }
+            if (nkb > 0) {
+                TS_BLOCK(true)
+                if (tr) tr_s[7] = gtimer();
+                sr = 1; sl = 1 % NL;
+                for (int kb = 1; kb < nkb; ++kb) {
+                    TS_BLOCK(false)
+                    if (kb & 1) umma_commit(&done[sr]);
+                    sr = (sr + 1 == NR) ? 0 : sr + 1;
+                    sl = (sl + 1 == NL) ? 0 : sl + 1;
                 }
-                if (kb & 1) umma_commit(&done[kb % NR]);
             }
+#undef TS_BLOCK
             umma_commit(&accum_bar);
             if (tr) tr_s[8] = gtimer();
         }

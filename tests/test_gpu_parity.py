@@ -112,16 +112,20 @@ def test_workspace_views_match_oracle(N):
     graph.f_log_probs(*batch)
     Tx, Ty, B = batch[0].shape[0], batch[2].shape[0], batch[0].shape[1]
     p = graph.plan(Tx, Ty, B)
+    PTx, PTy, _ = p.shape                         # the plan's (bucketed) shape: rows beyond Tx / Ty are masked padding
     lib = _lib.load()
     D, C = 16, 32
 
     def view(name, shape):
-        ptr = lib.nats_train_ws_view(ctypes.byref(graph.dims), Tx, Ty, B, ctypes.c_void_p(p.ws.data_ptr()),
+        pshape = {'ctx': (PTx, B, C), 'init_state': (B, D), 'dec_h': (PTy, B, D), 'dec_ctx': (PTy, B, C),
+                  'dec_alpha': (PTy, B, PTx)}[name]
+        ptr = lib.nats_train_ws_view(ctypes.byref(graph.dims), PTx, PTy, B, ctypes.c_void_p(p.ws.data_ptr()),
                                      name.encode())
         assert ptr
         off = (ptr - p.ws.data_ptr()) // 4
-        n = int(np.prod(shape))
-        return p.ws.view(torch.float32)[off:off + n].cpu().numpy().reshape(shape)
+        n = int(np.prod(pshape))
+        a = p.ws.view(torch.float32)[off:off + n].cpu().numpy().reshape(pshape)
+        return a[tuple(slice(0, d) for d in shape)]
 
     np.testing.assert_allclose(view('ctx', (Tx, B, C)), cache['ctx'], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(view('init_state', (B, D)), cache['init_state'], rtol=1e-4, atol=1e-6)
