@@ -378,8 +378,8 @@ def beam_run(nats, tparams, opts, w, steps, warm=True):
     bmod[0] = -1e9
     tparams['ff_logit_b'].set_value(bmod)
     try:
-        if warm:
-            nats.gen_sample(tparams, f_init, f_next, x, opts, None, 10, 4, False, False, True, 1.0, 1.0, 1.0)
+        if warm:                                     # same maxlen as the timed run: buffers of that size, kernels loaded
+            nats.gen_sample(tparams, f_init, f_next, x, opts, None, 10, steps, False, False, True, 1.0, 1.0, 1.0)
         torch.cuda.synchronize()
         t1 = time.time()
         f_init(x)
