@@ -276,6 +276,12 @@ def kernel_table(torch, run_step, steps=2):
     evs.sort()
     rows, cover = {}, -1e30
     for st, en, name in evs:
+        if 'nccl' in name.lower():
+            # collectives run on their own stream UNDER the compute kernels (and spin while they wait for the peers): they
+            # are listed with their raw duration and take no part in the exclusive-time attribution of the compute stream
+            r = rows.setdefault(name, [0.0, 0.0, 0])
+            r[1] += en - st; r[2] += 1
+            continue
         excl = max(0.0, en - max(st, cover))
         cover = max(cover, en)
         r = rows.setdefault(name, [0.0, 0.0, 0])

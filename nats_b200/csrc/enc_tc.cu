@@ -429,9 +429,57 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
             // K partials of this thread's gate elements, two elements at a time: all their loads are issued before the first
             // tag is looked at (one L2 round trip per pair); a word whose tag is not this step's yet is simply read again.
             // Sums in ascending chunk order: deterministic.
-            float ps0[EPT], ps1[EPT], ps2[EPT];
-#pragma unroll
-            for (int i = 0; i < EPT; ++i) ps0[i] = ps1[i] = ps2[i] = 0.f;
+            // With more than two elements per thread (batch 64) the registers do not hold every element's partial words,
+            // sums and outputs at once: each pair is then finished (gates + stores) right after its words arrived, and the
+            // saved gates are written immediately instead of after the release.
+            constexpr bool kDefer = EPT <= 2;
+            float o0[kDefer ? EPT : 1], o1[kDefer ? EPT : 1], o2[kDefer ? EPT : 1], o3[kDefer ? EPT : 1];
+            auto finish = [&](int i, float s0, float s1, float s2) {
+                const long long row = (long long)pos * n + eb[i];
+                const int d = dbase + ed[i];
+                float q0, q1, q2, q3 = 0.f;
+                if (!BWD) {                                                           // nats.py:336-356
+                    const float r = sigmoidf_(s0 + x0[i]), u = sigmoidf_(s1 + x1[i]);
+                    const float cnd = tanhf(s2 * r + x2[i]);
+                    const float hn = u * carry[i] + (1.f - u) * cnd;
+                    const float h = mk[i] * hn + (1.f - mk[i]) * carry[i];
+                    a.cc[row * C + dir * D + d] = h;
+                    a.lo[((long long)(dir * 2 + (s & 1)) * n + eb[i]) * a.Kp + d] = resid(h);
+                    carry[i] = h;
+                    csum[i] += mk[i] * h;
+                    q0 = r; q1 = u; q2 = cnd; q3 = s2;
+                } else {                                                              // reverse of the above
+                    const float m = mk[i], r = sr_[i], u = su_[i], cnd = sc_[i], pp = sp_[i], hp = x1[i];
+                    float dh = x0[i];
+                    if (s > 0) { dh += carry[i]; dh += s0; }
+                    if (a.mean_grad) dh += m * x2[i];
+                    const float dhn = m * dh;
+                    const float du = dhn * (hp - cnd);
+                    const float dc = dhn * (1.f - u);
+                    const float dpc_ = dc * (1.f - cnd * cnd);
+                    const float dp = dpc_ * r;
+                    const float dr = dpc_ * pp;
+                    const float dgr = dr * r * (1.f - r);
+                    const float dgu = du * u * (1.f - u);
+                    float* g = a.dG[dir] + row * D3 + d;
+                    g[0] = dgr; g[D] = dgu; g[2 * D] = dp;
+                    float* gl = a.lo + ((long long)(dir * 2 + (s & 1)) * n + eb[i]) * a.Kp + d;
+                    gl[0] = resid(dgr); gl[D] = resid(dgu); gl[2 * D] = resid(dp);
+                    carry[i] = (1.f - m) * dh + dhn * u;
+                    q0 = dgr; q1 = dgu; q2 = dpc_;
+                }
+                if (kDefer) {
+                    o0[kDefer ? i : 0] = q0; o1[kDefer ? i : 0] = q1; o2[kDefer ? i : 0] = q2; o3[kDefer ? i : 0] = q3;
+                } else if (!BWD) {
+                    if (a.r[dir]) {
+                        const long long o = row * D + d;
+                        a.r[dir][o] = q0; a.u[dir][o] = q1; a.c[dir][o] = q2; a.p[dir][o] = q3;
+                    }
+                } else {
+                    float* gx = a.dGx[dir] + row * D3 + d;
+                    gx[0] = q0; gx[D] = q1; gx[2 * D] = q2;
+                }
+            };
             if (s > 0) {
                 named_bar_sync(2, 128 + kGateThreads);       // (256 pollers spinning through the whole product would starve the TMEM warps' stores)
 #pragma unroll
@@ -464,63 +512,29 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
                         }
                         if (again && clock64() - t0 > kSpinLimit) __trap();
                     } while (again);
+                    if (stamp && s == 8 && gtid == 0 && i0 + 2 >= EPT) ENC_STAMP(4);
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         if (i0 + j < EPT && ev[i0 + j]) {
+                            float p0 = 0.f, p1 = 0.f, p2 = 0.f;                       // ascending chunk order: deterministic
 #pragma unroll
                             for (int k = 0; k < kMaxWords; k += NG) {
                                 if (k < nw) {
-                                    ps0[i0 + j] += __uint_as_float((uint32_t)w[j][k]);
+                                    p0 += __uint_as_float((uint32_t)w[j][k]);
                                     if (NG == 3) {
-                                        ps1[i0 + j] += __uint_as_float((uint32_t)w[j][k + NG - 2]);
-                                        ps2[i0 + j] += __uint_as_float((uint32_t)w[j][k + NG - 1]);
+                                        p1 += __uint_as_float((uint32_t)w[j][k + NG - 2]);
+                                        p2 += __uint_as_float((uint32_t)w[j][k + NG - 1]);
                                     }
                                 }
                             }
+                            finish(i0 + j, p0, p1, p2);
                         }
                     }
                 }
-                if (stamp && s == 8 && gtid == 0) ENC_STAMP(4);
-            }
-            float o0[EPT], o1[EPT], o2[EPT], o3[EPT];
+            } else {
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) {
-                o0[i] = o1[i] = o2[i] = o3[i] = 0.f;
-                if (ev[i]) {
-                    const float s0 = ps0[i], s1 = ps1[i], s2 = ps2[i];
-                    const long long row = (long long)pos * n + eb[i];
-                    const int d = dbase + ed[i];
-                    if (!BWD) {                                                       // nats.py:336-356
-                        const float r = sigmoidf_(s0 + x0[i]), u = sigmoidf_(s1 + x1[i]);
-                        const float cnd = tanhf(s2 * r + x2[i]);
-                        const float hn = u * carry[i] + (1.f - u) * cnd;
-                        const float h = mk[i] * hn + (1.f - mk[i]) * carry[i];
-                        a.cc[row * C + dir * D + d] = h;
-                        a.lo[((long long)(dir * 2 + (s & 1)) * n + eb[i]) * a.Kp + d] = resid(h);
-                        carry[i] = h;
-                        csum[i] += mk[i] * h;
-                        o0[i] = r; o1[i] = u; o2[i] = cnd; o3[i] = s2;
-                    } else {                                                          // reverse of the above
-                        const float m = mk[i], r = sr_[i], u = su_[i], cnd = sc_[i], pp = sp_[i], hp = x1[i];
-                        float dh = x0[i];
-                        if (s > 0) { dh += carry[i]; dh += s0; }
-                        if (a.mean_grad) dh += m * x2[i];
-                        const float dhn = m * dh;
-                        const float du = dhn * (hp - cnd);
-                        const float dc = dhn * (1.f - u);
-                        const float dpc_ = dc * (1.f - cnd * cnd);
-                        const float dp = dpc_ * r;
-                        const float dr = dpc_ * pp;
-                        const float dgr = dr * r * (1.f - r);
-                        const float dgu = du * u * (1.f - u);
-                        float* g = a.dG[dir] + row * D3 + d;
-                        g[0] = dgr; g[D] = dgu; g[2 * D] = dp;
-                        float* gl = a.lo + ((long long)(dir * 2 + (s & 1)) * n + eb[i]) * a.Kp + d;
-                        gl[0] = resid(dgr); gl[D] = resid(dgu); gl[2 * D] = resid(dp);
-                        carry[i] = (1.f - m) * dh + dhn * u;
-                        o0[i] = dgr; o1[i] = dgu; o2[i] = dpc_;
-                    }
-                }
+                for (int i = 0; i < EPT; ++i)
+                    if (ev[i]) finish(i, 0.f, 0.f, 0.f);
             }
             if (stamp && s == 8 && gtid == 0) ENC_STAMP(9);
             // every gate warp releases its own stores (no CTA-wide barrier in front of the fence): the tile counter counts
@@ -531,19 +545,22 @@ __global__ void __launch_bounds__(kThreads, 1) enc_tc_kernel(const __grid_consta
                 if (stamp && s == 8 && gtid == 0) ENC_STAMP(5);
             }
             // what no other CTA waits for
+            if (kDefer) {
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) {
-                if (ev[i]) {
-                    const long long row = (long long)pos * n + eb[i];
-                    const int d = dbase + ed[i];
-                    if (!BWD) {
-                        if (a.r[dir]) {
-                            const long long o = row * D + d;
-                            a.r[dir][o] = o0[i]; a.u[dir][o] = o1[i]; a.c[dir][o] = o2[i]; a.p[dir][o] = o3[i];
+                for (int i = 0; i < EPT; ++i) {
+                    if (ev[i]) {
+                        const long long row = (long long)pos * n + eb[i];
+                        const int d = dbase + ed[i];
+                        if (!BWD) {
+                            if (a.r[dir]) {
+                                const long long o = row * D + d;
+                                a.r[dir][o] = o0[kDefer ? i : 0]; a.u[dir][o] = o1[kDefer ? i : 0];
+                                a.c[dir][o] = o2[kDefer ? i : 0]; a.p[dir][o] = o3[kDefer ? i : 0];
+                            }
+                        } else {
+                            float* gx = a.dGx[dir] + row * D3 + d;
+                            gx[0] = o0[kDefer ? i : 0]; gx[D] = o1[kDefer ? i : 0]; gx[2 * D] = o2[kDefer ? i : 0];
                         }
-                    } else {
-                        float* gx = a.dGx[dir] + row * D3 + d;
-                        gx[0] = o0[i]; gx[D] = o1[i]; gx[2 * D] = o2[i];
                     }
                 }
             }
