@@ -371,7 +371,19 @@ int gemm_auto(const nats_ctx* ctx, cudaStream_t st, GemmProblem p, bool transA, 
         tiles = (long long)cdiv(p.M, bm) * cdiv(p.N, bn) * p.batch;
     }
     int splits = 1;
-    if (p.batch == 1 && tiles < ctx->num_sms && p.K >= 256 && scratch != nullptr) {
+    if (tc && p.batch == 1 && tiles >= ctx->num_sms && p.K >= 4096 && scratch != nullptr) {
+        // deep products whose tile count is not a multiple of the SM count (d[U|Ux] of the encoder: 192 tiles of K = 12768
+        // on 148 SMs = 2 waves for 1.3 waves of work): pick the split-K factor that minimises waves x (k-blocks per CTA +
+        // fixed cost) + the slab reduction, in microseconds (0.75 us per 128x128x32 k-block of 3xTF32, measured)
+        double best = 1e30;
+        for (int s2 = 1; s2 <= 4; ++s2) {
+            if ((long long)s2 * p.M * p.N > scratch_floats) break;
+            const long long waves = (tiles * s2 + ctx->num_sms - 1) / ctx->num_sms;
+            double t = (double)waves * ((double)p.K / s2 / 32.0 * 0.75 + 3.0);
+            if (s2 > 1) t += (double)(s2 + 1) * p.M * p.N * 4.0 / 5.0e6;
+            if (t < best) { best = t; splits = s2; }
+        }
+    } else if (p.batch == 1 && tiles < ctx->num_sms && p.K >= 256 && scratch != nullptr) {
         long long want = ((tc ? 1LL : 2LL) * ctx->num_sms + tiles - 1) / tiles;
         if (want > p.K / 128) want = p.K / 128;
         splits = (int)want;

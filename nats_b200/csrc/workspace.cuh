@@ -189,7 +189,7 @@ inline TrainWS carve_train(const nats_dims_t& d, int Tx, int Ty, int B, void* ba
     w.dcc = c.f(XB * C); w.dinit = c.f(B * D); w.dmean = c.f(B * C);
     for (int i = 0; i < 2; ++i) { w.dGe[i] = c.f(XB * 3 * D); w.dGex[i] = c.f(XB * 3 * D); }
     w.demb_x = c.f(XB * W);
-    w.gemm_scratch_floats = 8LL << 20;
+    w.gemm_scratch_floats = 16LL << 20;      // split-K slabs: up to 4 x [D,3D] at D = 1000 (the deep d[U|Ux] products)
     w.gemm_scratch = c.f(w.gemm_scratch_floats);
     { int64_t mx = V; if (3 * D > mx) mx = 3 * D; w.red_scratch = c.f(64 * mx); }
     w.enc_scratch_floats = enc_tc_scratch_floats(B, (int)D);
