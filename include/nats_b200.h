@@ -183,7 +183,7 @@ int nats_beam_distraction_scores(nats_ctx_t* ctx, void* stream,
 /* replaces: the full argsort over live_k*|V| candidate scores of nats.py:997-999.  Penalties and hypothesis scores are
  * constant per row, so the global best (k - dead_k) candidates are among each row's (k - dead_k) most probable words:
  * out_p[i, 0:k] / out_idx[i, 0:k] = the k largest probs[i, :] in descending order (ties: lower index first; -1 pads);
- * mask_unk != 0 treats entry 1 as 1e-20 (nats.py:975, use_unk=False). */
+ * mask_unk != 0 treats entry 1 as 1e-20 (nats.py:975, use_unk=False); NaN or negative entries count as 0. */
 int nats_beam_topk(nats_ctx_t* ctx, void* stream, const float* probs /* [n, n_words] */, int n, int n_words, int k,
                    int mask_unk, float* out_p /* [n,k] */, int32_t* out_idx /* [n,k] */);
 

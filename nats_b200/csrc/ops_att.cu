@@ -11,6 +11,9 @@
 #include "ops.cuh"
 #include "tc_common.cuh"
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 namespace nats {
 
 namespace {
@@ -256,6 +259,132 @@ __global__ void __launch_bounds__(kAttThreads) att_context_kernel(const __grid_c
     }
 }
 
+
+// ------------------------------------------------------------------ forward, beam search: ONE source for all rows
+// f_next of beam search runs k hypotheses against the encoder states of a single sentence (zero batch stride): the
+// [Tx, C] slab is the same for every row.  The per-(row, column slice) grid above re-streams it k times with a handful of
+// active lanes; here a cluster of 8 CTAs splits the source positions, every CTA walks its positions once for a 128-column
+// group and ALL rows (n <= 16 accumulator sets in registers), the 8 partial sums meet in distributed shared memory in a
+// fixed order, and rank r finishes 16 of the 128 columns (nats.py:541-546, 569-570).
+constexpr int kBcCluster = 8, kBcCols = 128, kBcMaxN = 16, kBcWarps = kAttThreads / 32;
+
+__global__ void __cluster_dims__(kBcCluster, 1, 1) __launch_bounds__(kAttThreads)
+    att_context_bcast_kernel(const __grid_constant__ AttFwd a, int chunk) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) float bc_sm[];
+    float* s_alpha = bc_sm;                                   // [n][chunk] normalised weights of this CTA's positions
+    float* s_part = bc_sm + (((size_t)a.n * chunk + 3) & ~(size_t)3);   // [n][128] this CTA's partial context (16-byte aligned)
+    __shared__ float s_mx[kBcMaxN], s_inv[kBcMaxN];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = blockIdx.x, c0 = blockIdx.y * kBcCols;
+    const int t0 = rank * chunk, t1 = min(a.Tx, t0 + chunk);
+    pdl_trigger();
+    pdl_wait();
+    // masked softmax statistics of every row over ALL positions (nats.py:537-540); max over valid positions only
+    for (int b = warp; b < a.n; b += kBcWarps) {
+        float mx = -INFINITY;
+        for (int t = lane; t < a.Tx; t += 32) {
+            const float mk = a.xmask ? a.xmask[(long long)t * a.n + b] : 1.f;
+            if (mk > 0.f) mx = fmaxf(mx, a.escore[(long long)b * a.Tx + t]);
+        }
+        mx = warp_max(mx);
+        if (mx == -INFINITY) mx = 0.f;
+        float sum = 0.f;
+        for (int t = lane; t < a.Tx; t += 32) {
+            const float mk = a.xmask ? a.xmask[(long long)t * a.n + b] : 1.f;
+            sum += expf(a.escore[(long long)b * a.Tx + t] - mx) * mk;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) { s_mx[b] = mx; s_inv[b] = 1.f / sum; }
+    }
+    for (int i = tid; i < a.n * kBcCols; i += kAttThreads) s_part[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < a.n * (t1 - t0); i += kAttThreads) {
+        const int b = i / (t1 - t0), tl = i - b * (t1 - t0), t = t0 + tl;
+        const float mk = a.xmask ? a.xmask[(long long)t * a.n + b] : 1.f;
+        const float al = expf(a.escore[(long long)b * a.Tx + t] - s_mx[b]) * mk * s_inv[b];
+        s_alpha[b * chunk + tl] = al;
+        if (blockIdx.y == 0) {
+            const float m = a.ymask ? a.ymask[b] : 1.f;
+            const long long o = (long long)b * a.Tx + t;
+            a.alpha_out[o] = al;
+            a.acc_alpha_out[o] = a.acc_alpha_in[o] + m * al;                               // nats.py:570
+        }
+    }
+    __syncthreads();
+
+    // c_raw[b, c] = sum_t alpha[b, t] * cc[t, c]: lane = 4 columns, warp = every 8th position of the chunk
+    float4 acc[kBcMaxN];
+#pragma unroll
+    for (int b = 0; b < kBcMaxN; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int col = c0 + lane * 4;
+    if (col < a.C) {
+        const float* base = a.cc + col;
+        int t = t0 + warp;
+        for (; t + 3 * kBcWarps < t1; t += 4 * kBcWarps) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = __ldg(reinterpret_cast<const float4*>(base + (long long)(t + j * kBcWarps) * a.cc_tstride));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int tl = t + j * kBcWarps - t0;
+#pragma unroll
+                for (int b = 0; b < kBcMaxN; ++b)
+                    if (b < a.n) {
+                        const float al = s_alpha[b * chunk + tl];
+                        acc[b].x = fmaf(al, v[j].x, acc[b].x); acc[b].y = fmaf(al, v[j].y, acc[b].y);
+                        acc[b].z = fmaf(al, v[j].z, acc[b].z); acc[b].w = fmaf(al, v[j].w, acc[b].w);
+                    }
+            }
+        }
+        for (; t < t1; t += kBcWarps) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)t * a.cc_tstride));
+            const int tl = t - t0;
+#pragma unroll
+            for (int b = 0; b < kBcMaxN; ++b)
+                if (b < a.n) {
+                    const float al = s_alpha[b * chunk + tl];
+                    acc[b].x = fmaf(al, v.x, acc[b].x); acc[b].y = fmaf(al, v.y, acc[b].y);
+                    acc[b].z = fmaf(al, v.z, acc[b].z); acc[b].w = fmaf(al, v.w, acc[b].w);
+                }
+        }
+    }
+    for (int w = 0; w < kBcWarps; ++w) {                      // warps add in order: deterministic
+        if (warp == w) {
+#pragma unroll
+            for (int b = 0; b < kBcMaxN; ++b)
+                if (b < a.n) {
+                    float4* p = reinterpret_cast<float4*>(s_part + b * kBcCols + lane * 4);
+                    float4 q = *p;
+                    q.x += acc[b].x; q.y += acc[b].y; q.z += acc[b].z; q.w += acc[b].w;
+                    *p = q;
+                }
+        }
+        __syncthreads();
+    }
+    cluster.sync();
+    // rank r finishes columns [16 r, 16 r + 16) of the group for every row
+    constexpr int kPer = kBcCols / kBcCluster;
+    if (tid < a.n * kPer) {
+        const int b = tid / kPer, cl = rank * kPer + (tid - b * kPer), gc = c0 + cl;
+        if (gc < a.C) {
+            float craw = 0.f;
+#pragma unroll
+            for (int q = 0; q < kBcCluster; ++q) craw += cluster.map_shared_rank(s_part, q)[b * kBcCols + cl];
+            const float m = a.ymask ? a.ymask[b] : 1.f;
+            const long long o = (long long)b * a.C + gc;
+            const float accc = a.acc_ctx_in[o];
+            const float cv = tanhf(__ldg(a.U_con + gc) * craw + __ldg(a.W_con + gc) * accc);   // nats.py:545-546
+            if (a.craw_out) a.craw_out[o] = craw;
+            a.ctx_out[o] = cv;
+            a.acc_ctx_out[o] = accc + m * cv;                                                   // nats.py:569
+        }
+    }
+    cluster.sync();                                           // remote reads done before any CTA exits
+}
+
 // ------------------------------------------------------------------ backward kernels
 __global__ void att_bwd_ctx_kernel(const __grid_constant__ AttBwd a) {
     pdl_trigger();
@@ -467,6 +596,7 @@ int attention_setup(const nats_ctx* ctx) {
     NATS_TRY(set_max_dyn_smem(att_context_kernel<2>, ctx->max_smem_optin, &lim));
     NATS_TRY(set_max_dyn_smem(att_context_kernel<1>, ctx->max_smem_optin, &lim));
     NATS_TRY(set_max_dyn_smem(att_context_kernel<0>, ctx->max_smem_optin, &lim));
+    NATS_TRY(set_max_dyn_smem(att_context_bcast_kernel, ctx->max_smem_optin, &lim));
     NATS_TRY(set_max_dyn_smem(att_bwd_softmax_kernel, ctx->max_smem_optin, &lim));
     NATS_TRY(set_max_dyn_smem(att_bwd_dalpha_kernel, ctx->max_smem_optin, &lim));
     NATS_TRY(set_max_dyn_smem(att_scores_kernel, ctx->max_smem_optin, &lim));
@@ -482,6 +612,17 @@ int attention_fwd(const nats_ctx* ctx, cudaStream_t st, const AttFwd& a_in) {
         dim3 grid(cdiv(a.Tx, kRowsPerCta), a.n);
         ProfScope ps(st, K_ATT_SCORES, 0.0, 4.0 * a.Tx * (a.pctx_bstride == 0 ? 1 : a.n) * a.A);
         NATS_CUDA_OK(launch_pdl(att_scores_kernel, grid, dim3(kAttThreads), 3 * a.A * sizeof(float), st, a));
+    }
+    static const int no_bcast = [] { const char* e = getenv("NATS_ATT_BCAST"); return e && atoi(e) == 0; }();
+    if (!no_bcast && a.cc_bstride == 0 && a.n <= kBcMaxN && (a.C & 3) == 0 && (a.cc_tstride & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(a.cc) & 15) == 0) {
+        const int chunk = cdiv(a.Tx, kBcCluster);
+        const size_t smem = ((((size_t)a.n * chunk + 3) & ~(size_t)3) + (size_t)a.n * kBcCols) * sizeof(float);
+        if (smem <= (size_t)g_att_dyn_limit) {
+            ProfScope ps(st, K_ATT_CONTEXT, 2.0 * a.Tx * a.n * a.C, 4.0 * ((double)a.Tx * a.C + 3.0 * a.n * a.Tx + 4.0 * a.n * a.C));
+            NATS_CUDA_OK(launch_pdl(att_context_bcast_kernel, dim3(kBcCluster, cdiv(a.C, kBcCols)), dim3(kAttThreads), smem, st, a, chunk));
+            return 0;
+        }
     }
     // column slices: as many CTAs as fit in ONE co-resident wave of 2 CTAs per SM (a partial second wave would run at
     // the per-CTA latency-bound rate and cost as much as the first)

@@ -2,6 +2,8 @@
 // bookkeeping copies (nats.py:1015-1023) on device.
 #include "ops.cuh"
 
+#include <cooperative_groups.h>
+
 namespace nats {
 
 namespace {
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict_
         for (int i = tid; i < V; i += 256) {
             float v = __ldg(row + i);
             if (mask_unk && i == 1) v = 1e-20f;                        // nats.py:975: next_p[:,1] = 1e-20
-            if (!(v == v)) v = 0.f;                                      // NaN never wins
+            if (!(v > 0.f)) v = 0.f;                                     // NaN / negatives count as 0 (never win)
             const bool after = (v < pv) || (v == pv && i > pi);
             if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
         }
@@ -315,10 +317,106 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict_
     }
 }
 
+// Beam-search shapes (a handful of rows, |V| <= 32768): a cluster of 8 CTAs per row.  Every lane holds 8 entries of the
+// row in REGISTERS (one read of the row instead of K); each warp picks its own K best with shuffles only, warp 0 merges
+// the CTA's 16 x K candidates, and the first warp of the cluster's first CTA merges the 8 x K survivors through
+// distributed shared memory.  A candidate is ONE 64-bit key, (bits of the probability) << 32 | ~index: probabilities are
+// >= +0 (anything else -- NaN, negatives -- counts as 0, in both kernels), so unsigned key order IS "value descending,
+// index ascending", the selection is branch-free, and key 0 means "no candidate".
+constexpr int kTopCluster = 8, kTopThreads = 512, kTopPer = 8, kTopMaxK = 32, kTopWarps = kTopThreads / 32;
+
+__device__ __forceinline__ unsigned long long cand_key(float v, int i) {
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+}
+
+// The K largest keys a warp holds in registers, in descending order; emit(r, key) runs on lane 0 for r = 0..K-1 (key 0
+// once the candidates run out).
+template <int NPER, class Emit>
+__device__ __forceinline__ void warp_select_topk(const unsigned long long (&key)[NPER], int K, int lane, Emit emit) {
+    unsigned long long prev = ~0ull;
+    for (int r = 0; r < K; ++r) {
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int q = 0; q < NPER; ++q) {
+            const unsigned long long c = key[q] < prev ? key[q] : 0ull;
+            best = c > best ? c : best;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (best == 0ull) {
+            if (lane == 0)
+                for (int q = r; q < K; ++q) emit(q, 0ull);
+            return;
+        }
+        if (lane == 0) emit(r, best);
+        prev = best;
+    }
+}
+
+__global__ void __cluster_dims__(kTopCluster, 1, 1) __launch_bounds__(kTopThreads)
+    beam_topk_cluster_kernel(const float* __restrict__ probs, int V, int K, int mask_unk, float* __restrict__ out_p,
+                             int32_t* __restrict__ out_idx) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ unsigned long long w_k[kTopWarps * kTopMaxK];
+    __shared__ unsigned long long c_k[kTopMaxK];
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* row = probs + (long long)blockIdx.y * V;
+    const int seglen = (V + kTopCluster - 1) / kTopCluster;
+    const int base = seg * seglen, end = min(V, base + seglen);
+    {
+        unsigned long long x[kTopPer];
+#pragma unroll
+        for (int k = 0; k < kTopPer; ++k) {
+            const int i = base + k * kTopThreads + tid;
+            float v = (i < end) ? __ldg(row + i) : 0.f;
+            if (mask_unk && i == 1) v = 1e-20f;                          // nats.py:975
+            if (!(v > 0.f)) v = 0.f;
+            x[k] = (i < end) ? cand_key(v, i) : 0ull;
+        }
+        warp_select_topk<kTopPer>(x, K, lane, [&](int r, unsigned long long c) { w_k[warp * K + r] = c; });
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long m[kTopWarps * kTopMaxK / 32];
+#pragma unroll
+        for (int q = 0; q < kTopWarps * kTopMaxK / 32; ++q) {
+            const int j = lane + 32 * q;
+            m[q] = (j < kTopWarps * K) ? w_k[j] : 0ull;
+        }
+        warp_select_topk<kTopWarps * kTopMaxK / 32>(m, K, lane, [&](int r, unsigned long long c) { c_k[r] = c; });
+    }
+    cluster.sync();
+    if (seg == 0 && warp == 0) {
+        unsigned long long m[kTopCluster * kTopMaxK / 32];
+#pragma unroll
+        for (int q = 0; q < kTopCluster * kTopMaxK / 32; ++q) {
+            const int j = lane + 32 * q;                                 // candidate j = (cta j / K, rank j % K)
+            m[q] = (j < kTopCluster * K) ? cluster.map_shared_rank(c_k, j / K)[j % K] : 0ull;
+        }
+        float* op = out_p + (long long)blockIdx.y * K;
+        int32_t* oi = out_idx + (long long)blockIdx.y * K;
+        warp_select_topk<kTopCluster * kTopMaxK / 32>(m, K, lane, [&](int r, unsigned long long c) {
+            op[r] = __uint_as_float((unsigned)(c >> 32));                // key 0 -> (0, -1): the pad of short rows
+            oi[r] = c ? (int)(0xffffffffu - (unsigned)c) : -1;
+        });
+    }
+    cluster.sync();                                                      // remote reads done before any CTA exits
+}
+
 }  // namespace
 
 int beam_topk(cudaStream_t st, const float* probs, int n, int V, int K, int mask_unk, float* out_p, int32_t* out_idx) {
     NATS_REQUIRE(n >= 1 && V >= 1 && K >= 1, "beam_topk shape");
+    static const int force_simple = [] { const char* e = getenv("NATS_TOPK_SIMPLE"); return e && atoi(e) != 0; }();
+    if (!force_simple && K <= kTopMaxK && V <= kTopCluster * kTopThreads * kTopPer && n <= 65535) {
+        beam_topk_cluster_kernel<<<dim3(kTopCluster, n), kTopThreads, 0, st>>>(probs, V, K, mask_unk, out_p, out_idx);
+        NATS_LAUNCH_OK();
+        return 0;
+    }
     beam_topk_kernel<<<n, 256, 0, st>>>(probs, V, K, mask_unk, out_p, out_idx);
     NATS_LAUNCH_OK();
     return 0;

@@ -1,6 +1,8 @@
 // ops_readout.cu -- softmax / cross-entropy rows of the readout (nats.py:763-770, 861-864).
 #include "ops.cuh"
 
+#include <cooperative_groups.h>
+
 namespace nats {
 
 namespace {
@@ -108,6 +110,58 @@ __global__ void __launch_bounds__(kRowThreads) softmax_sample_kernel(const float
     }
 }
 
+// Beam-search shapes (a handful of rows, no sampling, |V| <= 32768): one CTA per row leaves 138 SMs idle and walks the
+// row three times.  A cluster of 8 CTAs per row keeps its eighth of the row in registers (one read), and the row maximum
+// and the normaliser are combined through distributed shared memory in a fixed order (same value in every CTA).
+constexpr int kSmCluster = 8, kSmThreads = 512, kSmPer = 8;
+
+__global__ void __cluster_dims__(kSmCluster, 1, 1) __launch_bounds__(kSmThreads)
+    softmax_cluster_kernel(const float* __restrict__ logits, int V, float* __restrict__ probs) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float red[32];
+    __shared__ float s_part[2];
+    const int seg = blockIdx.x, tid = threadIdx.x;
+    const float* row = logits + (long long)blockIdx.y * V;
+    float* prow = probs + (long long)blockIdx.y * V;
+    const int seglen = (V + kSmCluster - 1) / kSmCluster;
+    const int base = seg * seglen, end = min(V, base + seglen);
+    float x[kSmPer];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kSmPer; ++k) {
+        const int i = base + k * kSmThreads + tid;
+        x[k] = (i < end) ? row[i] : -INFINITY;
+        mx = fmaxf(mx, x[k]);
+    }
+    mx = block_max(mx, red);
+    if (tid == 0) s_part[0] = mx;
+    cluster.sync();
+    float gmx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < kSmCluster; ++q) gmx = fmaxf(gmx, *cluster.map_shared_rank(&s_part[0], q));
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSmPer; ++k) {
+        const int i = base + k * kSmThreads + tid;
+        x[k] = (i < end) ? expf(x[k] - gmx) : 0.f;
+        s += x[k];
+    }
+    s = block_sum(s, red);
+    if (tid == 0) s_part[1] = s;
+    cluster.sync();
+    float gs = 0.f;
+#pragma unroll
+    for (int q = 0; q < kSmCluster; ++q) gs += *cluster.map_shared_rank(&s_part[1], q);
+    const float inv = 1.f / gs;
+#pragma unroll
+    for (int k = 0; k < kSmPer; ++k) {
+        const int i = base + k * kSmThreads + tid;
+        if (i < end) prow[i] = x[k] * inv;                               // nats.py:861
+    }
+    cluster.sync();                                                      // remote reads done before any CTA exits
+}
+
 }  // namespace
 
 int nll_rows(cudaStream_t st, const float* logits, int rows, int V, const int64_t* y, const float* ymask, float* lse,
@@ -134,6 +188,12 @@ int softmax_sample_rows(cudaStream_t st, const float* logits, int rows, int V, f
                         uint64_t seed, uint64_t step) {
     if (rows == 0) return 0;
     ProfScope ps(st, K_SOFTMAX_SAMPLE, 0.0, 16.0 * rows * V);
+    static const int force_simple = [] { const char* e = getenv("NATS_SOFTMAX_SIMPLE"); return e && atoi(e) != 0; }();
+    if (!force_simple && sample == nullptr && rows <= 148 && V <= kSmCluster * kSmThreads * kSmPer) {
+        softmax_cluster_kernel<<<dim3(kSmCluster, rows), kSmThreads, 0, st>>>(logits, V, probs);
+        NATS_LAUNCH_OK();
+        return 0;
+    }
     softmax_sample_kernel<<<rows, kRowThreads, 0, st>>>(logits, V, probs, sample, seed, step);
     NATS_LAUNCH_OK();
     return 0;

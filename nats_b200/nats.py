@@ -960,7 +960,8 @@ def build_sampler(tparams, options, trng=None):
         return tp.cpu().numpy(), ti.cpu().numpy()
 
     def next_device(y_d, ctx_d, pctx_d, st_d, ac_d, aa_d, Tx, n, outs):
-        """f_next entirely on device tensors (rows of ONE source: zero batch stride), outputs into preallocated `outs`"""
+        """f_next entirely on device tensors (rows of ONE source: zero batch stride), outputs into preallocated `outs`;
+        outs[1] = None skips the multinomial draw (beam search never reads it)"""
         ws, nbytes = ws_for(Tx, n)
         _lib.check(eng.lib.nats_sampler_next(
             eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(y_d), _ptr(ctx_d), C, 0, _ptr(pctx_d), A, 0,
@@ -1062,7 +1063,7 @@ def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_fac
     acc_ctx = [torch.zeros((k, C), **f32) for _ in range(2)]
     acc_alpha = [torch.zeros((k, Tx), **f32) for _ in range(2)]
     state[0][0].copy_(torch.from_numpy(numpy.ascontiguousarray(init_state, dtype='float32')).reshape(-1)[:D])
-    outs = [torch.empty((k, V), **f32), torch.empty((k,), dtype=torch.int64, device=dev), torch.empty((k, D), **f32),
+    outs = [torch.empty((k, V), **f32), None, torch.empty((k, D), **f32),
             torch.empty((k, Tx), **f32), torch.empty((k, C), **f32), torch.empty((k, C), **f32), torch.empty((k, Tx), **f32)]
     hist_alpha = [torch.zeros((k, maxlen, Tx), **f32) for _ in range(2)]
     hist_ctx = [torch.zeros((k, maxlen, C), **f32) for _ in range(2)] if distract else [None, None]
@@ -1080,7 +1081,11 @@ def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_fac
     top_p, top_i = torch.empty((k, k), **f32), torch.empty((k, k), **i32)
     pen = torch.zeros((3 * k,), **f32)
     scratch = torch.zeros((3 * k * maxlen + 16,), **f32)
-    flags = [(torch.zeros(8, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+    flags = [(torch.zeros(8, dtype=torch.int32).pin_memory(), torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
+    side = getattr(eng, '_flag_stream', None)                 # the flag copy must not sit between two steps' kernels
+    if side is None:
+        side = eng._flag_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
     for ii in range(maxlen):
         cur = ii & 1
         f_next.next_device(next_w, ctx_d, pctx_d, state[cur], acc_ctx[cur], acc_alpha[cur], Tx, k, outs)
@@ -1105,11 +1110,14 @@ def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_fac
             _ptr(hist_ctx[cur]), _ptr(hist_ctx[cur ^ 1]), _ptr(hist_state[cur]), _ptr(hist_state[cur ^ 1]), _ptr(out_alpha)),
             'nats_beam_advance')
         eng.launches += 4
-        buf, ev = flags[cur]
-        buf.copy_(counters, non_blocking=True)
-        ev.record()
+        buf, sel_ev, ev = flags[cur]
+        sel_ev.record(main)
+        side.wait_event(sel_ev)
+        with torch.cuda.stream(side):                         # `done` only ever goes 0 -> 1: a later step's value is fine
+            buf.copy_(counters, non_blocking=True)
+            ev.record(side)
         if ii > 0:                                            # the flag of the PREVIOUS step: its copy has long completed
-            pbuf, pev = flags[cur ^ 1]
+            pbuf, _, pev = flags[cur ^ 1]
             pev.synchronize()
             if int(pbuf[2]) != 0:
                 break

@@ -122,6 +122,33 @@ def test_config5_sampler_vs_oracle(N, params):
         y = rs.randint(2, 30000, size=n).astype('int64')
 
 
+def test_config5_softmax_cluster_matches_row_kernel(N, params):
+    """The beam-search f_next (no multinomial draw) normalises the |V| = 30000 rows with the 8-CTA cluster kernel, the
+    sampling f_next with one CTA per row: same probabilities (nats.py:861) up to the summation order."""
+    import torch
+    rs = np.random.RandomState(9)
+    x = np.concatenate([rs.randint(2, 30000, size=120), [0]]).astype('int64')[:, None]
+    tparams = N.init_tparams(params)
+    f_init, f_next = N.build_sampler(tparams, OPTS)
+    s0, ctx0 = f_init(x)
+    h = ctx0._nats_handle
+    eng = f_next.engine
+    n, Tx = 10, int(ctx0.shape[0])
+    f32 = dict(dtype=torch.float32, device=eng.device)
+    st = torch.from_numpy(np.tile(np.asarray(s0), [n, 1]) + 0.05 * rs.randn(n, 1000).astype('float32')).to(eng.device)
+    ac, aa = torch.zeros((n, 2000), **f32), torch.zeros((n, Tx), **f32)
+    y = torch.from_numpy(rs.randint(2, 30000, size=n).astype('int64')).to(eng.device)
+    res = []
+    for smp in (None, torch.empty((n,), dtype=torch.int64, device=eng.device)):
+        outs = [torch.empty((n, 30000), **f32), smp, torch.empty((n, 1000), **f32), torch.empty((n, Tx), **f32),
+                torch.empty((n, 2000), **f32), torch.empty((n, 2000), **f32), torch.empty((n, Tx), **f32)]
+        f_next.next_device(y, h.ctx_dev, h.pctx_dev, st, ac, aa, Tx, n, outs)
+        res.append(outs[0].cpu().numpy())
+    assert np.isfinite(res[0]).all()
+    np.testing.assert_allclose(res[0].sum(1), 1.0, rtol=1e-5)
+    np.testing.assert_allclose(res[0], res[1], rtol=2e-6, atol=1e-12)
+
+
 def test_config5_beam_vs_oracle(N, params):
     """10 beam steps, k = 10, all three distraction factors on, src_len 400: identical tokens, scores and penalty
     vectors (nats.py:981-999) as the literal restatement driven by the float64 oracle's f_init / f_next."""

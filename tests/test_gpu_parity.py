@@ -281,11 +281,19 @@ def test_beam_topk_matches_numpy(N):
     from nats_b200 import _lib
     eng = N.get_engine()
     rng = np.random.RandomState(5)
-    for (n, V, K) in [(7, 1000, 5), (3, 30011, 10), (2, 6, 6), (1, 3, 5)]:
+    # (…, 32768, …) is the largest row of the 8-CTA cluster kernel (one read of the row, candidates merged through
+    # distributed shared memory); 32769 columns or K = 33 take the one-CTA-per-row kernel
+    for (n, V, K) in [(7, 1000, 5), (3, 30011, 10), (2, 6, 6), (1, 3, 5), (10, 30000, 10), (2, 32768, 32), (2, 32769, 7),
+                      (3, 5000, 33), (4, 9, 10)]:
         p = rng.rand(n, V).astype('float32')
         p[:, 1] = 2.0                                   # the unk entry is the largest unless masked
         if V > 40:
             p[0, 17] = p[0, 33] = 1.5                   # a tie: lower index first
+        if V >= 5000:
+            p[1, :] = 0.25                              # a whole row of ties: indices 0, 1, 2, ... in order
+            p[1, V - 3] = 0.5
+            p[n - 1, 4000:4100] = 0.0                   # zeros are candidates like any other value
+            p[n - 1, V - 1] = 3.0                       # the last column (last CTA of the cluster) wins
         pd = torch.from_numpy(p).to(eng.device)
         for mask in (0, 1):
             op = torch.empty((n, K), dtype=torch.float32, device=eng.device)
