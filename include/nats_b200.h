@@ -204,10 +204,13 @@ int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, fl
  *   nats_beam_advance: state / acc_ctx / acc_alpha rows of the next step <- outputs of nats_sampler_next gathered by
  *     parents (:1015-1023); histories (alpha always, ctx / state when hist_ctx_src != NULL) <- history of the parent + the
  *     current vectors; out_alpha [k,len_cap,Tx] receives the attention history of the hypotheses retired in this step.
- * The host reads `done` (asynchronously) to stop early and copies the result buffers once at the end. */
+ *     host_counters (NULL = off): page-locked HOST memory the device can address (cudaHostAlloc under unified addressing),
+ *     int32[8]; the kernel stores the five counters there as well, so the host polls `done` without any copy.
+ * The host reads `done` one or two steps late to stop early and copies the result buffers once at the end. */
 int nats_beam_select(nats_ctx_t* ctx, void* stream, const float* top_p, const int32_t* top_i, const float* pen,
                      int k, int maxlen, int step, int32_t* counters, float* scores, int32_t* tokens, int32_t* parents,
-                     int64_t* next_w, int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent);
+                     int64_t* next_w, int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent,
+                     int32_t* host_counters);
 int nats_beam_advance(nats_ctx_t* ctx, void* stream, const int32_t* parents, const int32_t* fin_parent,
                       const int32_t* counters, int k, int len_cap, int step, int Tx, int C, int D,
                       const float* state_o, float* state_n, const float* acc_ctx_o, float* acc_ctx_n,

@@ -64,7 +64,7 @@ SIGNATURES = {
                                              _P, _P, _P, c_float, c_float, c_float, _P, _P]),
     'nats_beam_topk': (c_int, [c_void_p, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     'nats_beam_reorder_append': (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int]),
-    'nats_beam_select': (c_int, [c_void_p, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'nats_beam_select': (c_int, [c_void_p, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'nats_beam_advance': (c_int, [c_void_p, _P] + [_P] * 3 + [c_int] * 6 + [_P] * 16),
     'nats_debug_gemm': (c_int, [c_void_p, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, c_int,
                                 _P, c_int, c_int, c_int, c_int64, c_int64, c_int64]),

@@ -93,6 +93,7 @@ int nats_ctx_create(int device, nats_ctx_t** out) {
     c->dev_scratch = nullptr;
     NATS_CUDA_OK(cudaMalloc(&c->dev_scratch, kCtxScratchFloats * sizeof(float)));
     int r = attention_setup(c);
+    if (r == 0) r = narrow_proj_setup(c);
     if (r == 0) r = tc_gemm_setup();
     if (r == 0) r = tma_gemm_setup();
     if (r == 0) r = enc_tc_setup(c);
@@ -430,16 +431,27 @@ int nats_sampler_next(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, co
     NATS_TRY(decoder_step_forward(ctx, st, *dims, params, s));
 
     // readout (nats.py:850-861)
-    GemmProblem p = gemm_problem(state_out, D, params + o.lstm_W, W, w.L, W, n, W, D);
-    p.bias = params + o.lstm_b;
-    NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
-    p = gemm_problem(w.emb_y, W, params + o.prev_W, W, w.L, W, n, W, W);
-    p.bias = params + o.prev_b; p.accumulate = 1;
-    NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
-    p = gemm_problem(ctxs, C, params + o.ctxr_W, W, w.L, W, n, W, C);
-    p.bias = params + o.ctxr_b; p.accumulate = 1;
-    NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
-    NATS_TRY(tanh_inplace(st, w.L, (long long)n * W));
+    NarrowProj np;
+    memset(&np, 0, sizeof(np));
+    np.x[0] = state_out; np.ldx[0] = D; np.W[0] = params + o.lstm_W; np.ldw[0] = W; np.bias[0] = params + o.lstm_b; np.K[0] = D;
+    np.x[1] = w.emb_y;   np.ldx[1] = W; np.W[1] = params + o.prev_W; np.ldw[1] = W; np.bias[1] = params + o.prev_b; np.K[1] = W;
+    np.x[2] = ctxs;      np.ldx[2] = C; np.W[2] = params + o.ctxr_W; np.ldw[2] = W; np.bias[2] = params + o.ctxr_b; np.K[2] = C;
+    np.n = n; np.N = W; np.out = w.L; np.ldo = W; np.act_tanh = 1;
+    GemmProblem p;
+    if (narrow_proj_eligible(np)) {
+        NATS_TRY(narrow_proj(st, np));                          // one launch: three products + biases + tanh, exact fp32
+    } else {
+        p = gemm_problem(state_out, D, params + o.lstm_W, W, w.L, W, n, W, D);
+        p.bias = params + o.lstm_b;
+        NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
+        p = gemm_problem(w.emb_y, W, params + o.prev_W, W, w.L, W, n, W, W);
+        p.bias = params + o.prev_b; p.accumulate = 1;
+        NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
+        p = gemm_problem(ctxs, C, params + o.ctxr_W, W, w.L, W, n, W, C);
+        p.bias = params + o.ctxr_b; p.accumulate = 1;
+        NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
+        NATS_TRY(tanh_inplace(st, w.L, (long long)n * W));
+    }
     p = gemm_problem(w.L, W, params + o.logit_W, V, w.logits, V, n, V, W);
     p.bias = params + o.logit_b;
     NATS_TRY(gemm_auto(ctx, st, p, false, false, w.gemm_scratch, w.gemm_scratch_floats));
@@ -503,12 +515,13 @@ int nats_beam_reorder_append(nats_ctx_t* ctx, void* stream, const float* src, fl
 
 int nats_beam_select(nats_ctx_t* ctx, void* stream, const float* top_p, const int32_t* top_i, const float* pen, int k,
                      int maxlen, int step, int32_t* counters, float* scores, int32_t* tokens, int32_t* parents,
-                     int64_t* next_w, int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent) {
+                     int64_t* next_w, int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent,
+                     int32_t* host_counters) {
     (void)ctx;
     NATS_REQUIRE(top_p && top_i && counters && scores && tokens && parents && next_w && out_tokens && out_len && out_score &&
                      fin_parent, "null argument");
     return beam_select(reinterpret_cast<cudaStream_t>(stream), top_p, top_i, pen, k, maxlen, step, counters, scores, tokens,
-                       parents, reinterpret_cast<long long*>(next_w), out_tokens, out_len, out_score, fin_parent);
+                       parents, reinterpret_cast<long long*>(next_w), out_tokens, out_len, out_score, fin_parent, host_counters);
 }
 
 int nats_beam_advance(nats_ctx_t* ctx, void* stream, const int32_t* parents, const int32_t* fin_parent,

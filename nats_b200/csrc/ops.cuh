@@ -85,6 +85,19 @@ int tma_gemm_get_ts();
 
 // ------------------------------------------------------------------ small elementwise / reductions
 int tanh_inplace(cudaStream_t st, float* x, long long n);
+// out[n,N] = act(sum_p x_p[n,K_p].W_p[K_p,N] + sum_p bias_p): few rows, narrow output (ops_readout.cu); unused parts K = 0
+struct NarrowProj {
+    const float* x[3]; long long ldx[3];
+    const float* W[3]; long long ldw[3];
+    const float* bias[3];
+    int K[3];
+    int n, N;
+    float* out; long long ldo;
+    int act_tanh;
+};
+int narrow_proj_setup(const nats_ctx* ctx);   // one-time kernel attribute (shared-memory opt-in)
+bool narrow_proj_eligible(const NarrowProj& a);
+int narrow_proj(cudaStream_t st, const NarrowProj& a);
 // dst[i] = g[i] * (1 - y[i]^2)
 int dtanh(cudaStream_t st, const float* g, const float* y, float* dst, long long n);
 // dst[b,j] = (a[b,j] + sum_s part[s][b][j]) * (1 - y[b,j]^2)   (d init_state path)
@@ -182,7 +195,7 @@ int beam_reorder_append(cudaStream_t st, const float* src, float* dst, const flo
 // device-resident bookkeeping of one beam step (nats.py:976-1066): see ops_beam.cu
 int beam_select(cudaStream_t st, const float* top_p, const int32_t* top_i, const float* pen, int k, int maxlen, int step,
                 int32_t* counters, float* scores, int32_t* tokens, int32_t* parents, long long* next_w,
-                int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent);
+                int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent, int32_t* host_counters);
 int beam_advance(cudaStream_t st, const int32_t* parents, const int32_t* fin_parent, const int32_t* counters, int k,
                  int len_cap, int step, int Tx, int C, int D, const float* state_o, float* state_n, const float* acc_ctx_o,
                  float* acc_ctx_n, const float* acc_alpha_o, float* acc_alpha_n, const float* cur_alpha, const float* cur_ctx,

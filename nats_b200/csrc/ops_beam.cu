@@ -117,6 +117,7 @@ constexpr int kMaxBeam = 32;
 //   counters[0] live_k, [1] dead_k, [2] done flag (set when live_k < 1 or dead_k >= k, :1057), [3] finished so far,
 //   [4] index of the last step that was carried out (steps issued after `done` change nothing)
 //   scores / tokens are ping-pong buffers selected by the step parity; tokens rows hold `step` words on entry
+//   host_counters (optional): device-visible pinned host memory that receives the same five words
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) beam_select_kernel(const float* __restrict__ top_p, const int32_t* __restrict__ top_i,
                                                          const float* __restrict__ pen, int k, int maxlen, int step,
@@ -124,10 +125,12 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const float* __restrict
                                                          int32_t* __restrict__ tokens, int32_t* __restrict__ parents,
                                                          long long* __restrict__ next_w, int32_t* __restrict__ out_tokens,
                                                          int32_t* __restrict__ out_len, float* __restrict__ out_score,
-                                                         int32_t* __restrict__ fin_parent) {
+                                                         int32_t* __restrict__ fin_parent, int32_t* host_counters) {
     __shared__ float s_rank[kMaxBeam * kMaxBeam];
     __shared__ float s_cost[kMaxBeam * kMaxBeam];
+    __shared__ int s_word[kMaxBeam * kMaxBeam];                       // top_i, read once (every later use is on the serial path)
     __shared__ int s_sel[kMaxBeam];
+    __shared__ int s_slot[kMaxBeam];                                  // destination row of selected candidate r; bit 30: retired
     const int lane = threadIdx.x;
     const int cur = step & 1, nxt = cur ^ 1;
     const float* sc_in = scores + cur * k;
@@ -141,9 +144,11 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const float* __restrict
     const int ncand = live_k * k;
     for (int e = lane; e < k * k; e += 32) {
         float cost = INFINITY, rank = INFINITY;
+        const int word = (e < ncand) ? top_i[e] : -1;
+        s_word[e] = word;
         if (e < ncand) {
             const int r = e / k;
-            if (top_i[e] >= 0) {
+            if (word >= 0) {
                 cost = sc_in[r] - logf(top_p[e]);                     // nats.py:976
                 rank = cost;
                 if (pen != nullptr && step > 0) rank = cost + pen[r] + pen[k + r] + pen[2 * k + r];     // :997
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const float* __restrict
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (bi == 0x7fffffff || top_i[bi] < 0) break;                 // fewer valid candidates than n_keep
+        if (bi == 0x7fffffff || s_word[bi] < 0) break;                // fewer valid candidates than n_keep
         if (lane == 0) { s_sel[r] = bi; s_rank[bi] = __int_as_float(0x7fc00000); }      // consumed: NaN never compares smaller or equal
         nsel = r + 1;
         __syncwarp();
@@ -176,65 +181,96 @@ __global__ void __launch_bounds__(32) beam_select_kernel(const float* __restrict
     int new_live = 0, nfin = counters[3], ndead = dead_k, fin_now = 0;
     for (int r = 0; r < nsel; ++r) {                                  // rank order, as the reference's zip loop (:1010-1052)
         const int e = s_sel[r];
-        const int ti = e / k, wi = top_i[e];
+        const int ti = e / k, wi = s_word[e];
         const float ci = s_cost[e];
         if (wi == 0) {
-            int32_t* dst = out_tokens + (long long)nfin * maxlen;
-            for (int t = lane; t < step; t += 32) dst[t] = tk_in[(long long)ti * maxlen + t];
-            if (lane == 0) { dst[step] = 0; out_len[nfin] = step + 1; out_score[nfin] = ci; fin_parent[fin_now] = ti; }
+            if (lane == 0) {
+                out_tokens[(long long)nfin * maxlen + step] = 0; out_len[nfin] = step + 1; out_score[nfin] = ci;
+                fin_parent[fin_now] = ti; s_slot[r] = nfin | (1 << 30);
+            }
             ++nfin; ++ndead; ++fin_now;
         } else {
-            int32_t* dst = tk_out + (long long)new_live * maxlen;
-            for (int t = lane; t < step; t += 32) dst[t] = tk_in[(long long)ti * maxlen + t];
-            if (lane == 0) { dst[step] = wi; sc_out[new_live] = ci; parents[new_live] = ti; next_w[new_live] = wi; }
+            if (lane == 0) {
+                tk_out[(long long)new_live * maxlen + step] = wi; sc_out[new_live] = ci; parents[new_live] = ti;
+                next_w[new_live] = wi; s_slot[r] = new_live;
+            }
             ++new_live;
         }
     }
     __syncwarp();
+    // the word histories of all selected candidates in one flat loop (independent loads, not one row after the other)
+    for (int idx = lane; idx < nsel * step; idx += 32) {
+        const int r = idx / step, t = idx - r * step;
+        const int slot = s_slot[r], ti = s_sel[r] / k;
+        int32_t* dst = (slot & (1 << 30)) ? out_tokens + (long long)(slot & ~(1 << 30)) * maxlen : tk_out + (long long)slot * maxlen;
+        dst[t] = tk_in[(long long)ti * maxlen + t];
+    }
+    __syncwarp();
     if (lane == 0) {
+        const int done = (new_live < 1 || ndead >= k) ? 1 : 0;
         counters[0] = new_live; counters[1] = ndead; counters[3] = nfin; counters[4] = step;
-        if (new_live < 1 || ndead >= k) counters[2] = 1;
+        if (done) counters[2] = 1;
+        if (host_counters != nullptr) {                               // mapped pinned host memory: the host polls it, no copy
+            volatile int32_t* h = host_counters;
+            h[0] = new_live; h[1] = ndead; h[3] = nfin; h[4] = step; h[2] = done;
+            __threadfence_system();
+        }
     }
 }
 
-// rows of the next step <- rows of their parents: dst[j,:] = src[parent[j],:] for the three state buffers of f_next
-__global__ void __launch_bounds__(256) beam_gather_kernel(const int32_t* __restrict__ parent, const float* __restrict__ s0,
-                                                          float* __restrict__ d0, int n0, const float* __restrict__ s1,
-                                                          float* __restrict__ d1, int n1, const float* __restrict__ s2,
-                                                          float* __restrict__ d2, int n2) {
-    const int j = blockIdx.x, par = parent[j];
-    if (par < 0) return;
-    const float* src = blockIdx.y == 0 ? s0 : (blockIdx.y == 1 ? s1 : s2);
-    float* dst = blockIdx.y == 0 ? d0 : (blockIdx.y == 1 ? d1 : d2);
-    const int n = blockIdx.y == 0 ? n0 : (blockIdx.y == 1 ? n1 : n2);
-    for (int t = threadIdx.x; t < n; t += 256) dst[(long long)j * n + t] = src[(long long)par * n + t];
-}
+// One launch for all the copies of a beam step (nats.py:1015-1023, 1040); blockIdx.z selects the job:
+//   0..2  history of the next step's row j <- history of its parent + the current vector (alpha; ctx and state when kept)
+//   3     attention history of the hypotheses that retired in this step -> result slot (slots are assigned in order)
+//   4     state / acc_ctx / acc_alpha rows of the next step <- f_next outputs of the parents (blockIdx.y = buffer)
+struct BeamAdvance {
+    const int32_t* parents; const int32_t* fin_parent; const int32_t* counters;
+    const float* hist_src[3]; float* hist_dst[3]; const float* cur[3]; int dim[3];
+    const float* row_src[3]; float* row_dst[3]; int row_dim[3];
+    float* out_alpha;
+    int k, len_cap, step;
+};
 
-// attention history of the hypotheses that retired in this step (nats.py:1040): out[f] = history(parent) + current alpha
-__global__ void __launch_bounds__(256) beam_finish_alpha_kernel(const int32_t* __restrict__ fin_parent,
-                                                                const int32_t* __restrict__ counters,
-                                                                const float* __restrict__ hist, const float* __restrict__ cur,
-                                                                float* __restrict__ out, int len_cap, int step, int Tx) {
-    const int f = blockIdx.x, s = blockIdx.y;
-    const int par = fin_parent[f];
-    if (par < 0) return;
-    int nf_before = counters[3];
-    for (int q = 0; q < gridDim.x; ++q)                               // slots are assigned in order: count this step's retirements
-        if (fin_parent[q] >= 0) --nf_before;
-    const float* from = (s < step) ? hist + ((long long)par * len_cap + s) * Tx : cur + (long long)par * Tx;
-    float* to = out + ((long long)(nf_before + f) * len_cap + s) * Tx;
-    for (int t = threadIdx.x; t < Tx; t += 256) to[t] = from[t];
+__global__ void __launch_bounds__(256) beam_advance_kernel(const __grid_constant__ BeamAdvance a) {
+    const int j = blockIdx.x, s = blockIdx.y, job = blockIdx.z;
+    if (job < 4 && s > a.step) return;                                // the grid is at least 3 deep for job 4
+    if (job < 3) {
+        if (a.hist_src[job] == nullptr) return;
+        const int par = a.parents[j];
+        if (par < 0) return;                                          // row not alive after this step
+        const int dim = a.dim[job];
+        const float* from = (s < a.step) ? a.hist_src[job] + ((long long)par * a.len_cap + s) * dim : a.cur[job] + (long long)par * dim;
+        float* to = a.hist_dst[job] + ((long long)j * a.len_cap + s) * dim;
+        for (int t = threadIdx.x; t < dim; t += 256) to[t] = from[t];
+    } else if (job == 3) {
+        const int par = a.fin_parent[j];
+        if (par < 0) return;
+        int nf_before = a.counters[3];
+        for (int q = 0; q < a.k; ++q)                                 // count this step's retirements
+            if (a.fin_parent[q] >= 0) --nf_before;
+        const int Tx = a.dim[0];
+        const float* from = (s < a.step) ? a.hist_src[0] + ((long long)par * a.len_cap + s) * Tx : a.cur[0] + (long long)par * Tx;
+        float* to = a.out_alpha + ((long long)(nf_before + j) * a.len_cap + s) * Tx;
+        for (int t = threadIdx.x; t < Tx; t += 256) to[t] = from[t];
+    } else {
+        if (s >= 3) return;
+        const int par = a.parents[j];
+        if (par < 0) return;
+        const int n = a.row_dim[s];
+        const float* src = a.row_src[s] + (long long)par * n;
+        float* dst = a.row_dst[s] + (long long)j * n;
+        for (int t = threadIdx.x; t < n; t += 256) dst[t] = src[t];
+    }
 }
 
 }  // namespace
 
 int beam_select(cudaStream_t st, const float* top_p, const int32_t* top_i, const float* pen, int k, int maxlen, int step,
                 int32_t* counters, float* scores, int32_t* tokens, int32_t* parents, long long* next_w,
-                int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent) {
+                int32_t* out_tokens, int32_t* out_len, float* out_score, int32_t* fin_parent, int32_t* host_counters) {
     NATS_REQUIRE(k >= 1 && k <= kMaxBeam && step >= 0 && step < maxlen, "beam_select shape (beam <= 32)");
     ProfScope ps(st, K_BEAM);
     beam_select_kernel<<<1, 32, 0, st>>>(top_p, top_i, pen, k, maxlen, step, counters, scores, tokens, parents, next_w,
-                                         out_tokens, out_len, out_score, fin_parent);
+                                         out_tokens, out_len, out_score, fin_parent, host_counters);
     NATS_LAUNCH_OK();
     return 0;
 }
@@ -246,20 +282,19 @@ int beam_advance(cudaStream_t st, const int32_t* parents, const int32_t* fin_par
                  float* hist_ctx_dst, const float* hist_state_src, float* hist_state_dst, float* out_alpha) {
     NATS_REQUIRE(k >= 1 && step >= 0 && step < len_cap, "beam_advance shape");
     ProfScope ps(st, K_BEAM);
-    beam_gather_kernel<<<dim3(k, 3), 256, 0, st>>>(parents, state_o, state_n, D, acc_ctx_o, acc_ctx_n, C, acc_alpha_o,
-                                                   acc_alpha_n, Tx);
+    BeamAdvance a;
+    memset(&a, 0, sizeof(a));
+    a.parents = parents; a.fin_parent = fin_parent; a.counters = counters;
+    a.hist_src[0] = hist_alpha_src; a.hist_dst[0] = hist_alpha_dst; a.cur[0] = cur_alpha; a.dim[0] = Tx;
+    a.hist_src[1] = hist_ctx_src;   a.hist_dst[1] = hist_ctx_dst;   a.cur[1] = cur_ctx;   a.dim[1] = C;
+    a.hist_src[2] = hist_ctx_src != nullptr ? hist_state_src : nullptr; a.hist_dst[2] = hist_state_dst; a.cur[2] = cur_state; a.dim[2] = D;
+    a.row_src[0] = state_o;     a.row_dst[0] = state_n;     a.row_dim[0] = D;
+    a.row_src[1] = acc_ctx_o;   a.row_dst[1] = acc_ctx_n;   a.row_dim[1] = C;
+    a.row_src[2] = acc_alpha_o; a.row_dst[2] = acc_alpha_n; a.row_dim[2] = Tx;
+    a.out_alpha = out_alpha; a.k = k; a.len_cap = len_cap; a.step = step;
+    const int gy = step + 1 < 3 ? 3 : step + 1;
+    beam_advance_kernel<<<dim3(k, gy, 5), 256, 0, st>>>(a);
     NATS_LAUNCH_OK();
-    beam_finish_alpha_kernel<<<dim3(k, step + 1), 256, 0, st>>>(fin_parent, counters, hist_alpha_src, cur_alpha, out_alpha,
-                                                                len_cap, step, Tx);
-    NATS_LAUNCH_OK();
-    beam_reorder_kernel<<<dim3(k, step + 1), 256, 0, st>>>(hist_alpha_src, hist_alpha_dst, cur_alpha, parents, len_cap, step, Tx);
-    NATS_LAUNCH_OK();
-    if (hist_ctx_src != nullptr) {
-        beam_reorder_kernel<<<dim3(k, step + 1), 256, 0, st>>>(hist_ctx_src, hist_ctx_dst, cur_ctx, parents, len_cap, step, C);
-        NATS_LAUNCH_OK();
-        beam_reorder_kernel<<<dim3(k, step + 1), 256, 0, st>>>(hist_state_src, hist_state_dst, cur_state, parents, len_cap, step, D);
-        NATS_LAUNCH_OK();
-    }
     return 0;
 }
 

@@ -162,7 +162,176 @@ __global__ void __cluster_dims__(kSmCluster, 1, 1) __launch_bounds__(kSmThreads)
     cluster.sync();                                                      // remote reads done before any CTA exits
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Few rows x narrow output (f_next's readout hidden layer, nats.py:850-857):
+//     out[n, N] = act( sum_p x_p[n, K_p] . W_p[K_p, N] + sum_p bias_p ),   n <= 16, N <= 128, up to 3 parts.
+// Three library GEMMs + two slab reductions + a tanh are pure launch latency at this size (~30 us per beam step); here a
+// cluster of 8 CTAs splits the concatenated K, 16 warps x (4 columns per lane) per CTA accumulate in exact fp32 FFMA, the
+// partial sums meet in distributed shared memory in a fixed order and rank r finishes 16 columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int kNpCluster = 8, kNpThreads = 512, kNpWarps = kNpThreads / 32, kNpCols = 128, kNpMaxRows = 16;
+
+// Code size matters here: the kernel runs for a few microseconds on 8 SMs and every instruction is fetched cold.  A first
+// version with the weight loads unrolled 6-12 deep in registers and the parts selected per row was 58 KB of straight-line
+// SASS and ran 25 us, bound by instruction fetch (time fell with the number of rows n because whole blocks were skipped).
+// Now the CTA's slice of [W_0; W_1; W_2] is staged in shared memory by a small copy loop (all loads in flight), and the
+// product is a rolled loop over weight rows: per row and warp one 16-byte read per lane (4 columns), <= 4 broadcast reads
+// of the 16 x values of that k, 64 FFMA.
+__global__ void __cluster_dims__(kNpCluster, 1, 1) __launch_bounds__(kNpThreads)
+    narrow_proj_kernel(const __grid_constant__ NarrowProj a, int rows_per_cta) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) float np_sm[];
+    float* ws = np_sm;                                            // [rows_per_cta][N] this CTA's rows of [W_0; W_1; W_2]
+    const size_t ws_floats = max((size_t)rows_per_cta * a.N, (size_t)kNpWarps * a.n * kNpCols);
+    float* xs = ws + ws_floats;                                   // [rows_per_cta][16] the same rows of [x_0 | x_1 | x_2]
+    float* red = xs + (size_t)rows_per_cta * kNpMaxRows;          // [n][128] partial sums of this CTA
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = blockIdx.x;
+    const int Kt = a.K[0] + a.K[1] + a.K[2];
+    const int j0 = rank * rows_per_cta, j1 = min(Kt, j0 + rows_per_cta);
+    const int n4 = a.N >> 2;
+#ifdef NARROW_TRACE
+    unsigned long long ts[10]; int nts = 0;
+#define NP_STAMP() do { if (tid == 0 && rank == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ts[nts++] = t_; } } while (0)
+#else
+#define NP_STAMP() do { } while (0)
+#endif
+    NP_STAMP();
+    pdl_trigger();
+    // weights do not depend on the predecessor: staged before the dependency wait
+    int base = 0;
+#pragma unroll 1
+    for (int p = 0; p < 3; ++p) {
+        const int lo = max(j0, base), hi = min(j1, base + a.K[p]);        // rows of part p in this CTA's slice
+        const float* W = a.W[p];
+        const long long ldw = a.ldw[p];
+#pragma unroll 4
+        for (int i = tid; i < (hi - lo) * n4; i += kNpThreads) {
+            const int r = i / n4, c4 = i - r * n4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(W + (long long)(lo + r - base) * ldw) + c4);
+            reinterpret_cast<float4*>(ws + (size_t)(lo + r - j0) * a.N)[c4] = v;
+        }
+        base += a.K[p];
+    }
+    NP_STAMP();
+    pdl_wait();
+    base = 0;
+#pragma unroll 1
+    for (int p = 0; p < 3; ++p) {
+        const int lo = max(j0, base), hi = min(j1, base + a.K[p]);
+        const float* x = a.x[p];
+        const long long ldx = a.ldx[p];
+#pragma unroll 4
+        for (int i = tid; i < (hi - lo) * kNpMaxRows; i += kNpThreads) {
+            const int r = i >> 4, b = i & (kNpMaxRows - 1);
+            xs[(size_t)(lo + r - j0) * kNpMaxRows + b] = (b < a.n) ? x[(long long)b * ldx + (lo + r - base)] : 0.f;
+        }
+        base += a.K[p];
+    }
+    __syncthreads();
+    NP_STAMP();
+    float4 acc[kNpMaxRows];
+#pragma unroll
+    for (int b = 0; b < kNpMaxRows; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nq = (a.n + 3) >> 2;
+    if (lane < n4) {
+#pragma unroll 2
+        for (int jl = warp; jl < j1 - j0; jl += kNpWarps) {
+            const float4 w = reinterpret_cast<const float4*>(ws + (size_t)jl * a.N)[lane];
+            const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)jl * kNpMaxRows);
+#pragma unroll
+            for (int q = 0; q < kNpMaxRows / 4; ++q)
+                if (q < nq) {
+                    const float4 x4 = xr[q];
+                    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float4& c = acc[4 * q + e];
+                        c.x = fmaf(xv[e], w.x, c.x); c.y = fmaf(xv[e], w.y, c.y); c.z = fmaf(xv[e], w.z, c.z); c.w = fmaf(xv[e], w.w, c.w);
+                    }
+                }
+        }
+    }
+    NP_STAMP();
+    // the 16 warps' partial sums: each warp parks its own in the (now free) weight stage, then every (row, column) adds
+    // the 16 values in warp order -- deterministic, one barrier instead of 16 serial rounds
+    __syncthreads();                                              // all warps are done reading ws
+    float* part = ws;                                             // [16 warps][n][128]
+    if (lane < n4) {
+#pragma unroll
+        for (int b = 0; b < kNpMaxRows; ++b)
+            if (b < a.n) reinterpret_cast<float4*>(part + ((size_t)warp * a.n + b) * kNpCols)[lane] = acc[b];
+    }
+    __syncthreads();
+    for (int i = tid; i < a.n * a.N; i += kNpThreads) {
+        const int b = i / a.N, c = i - b * a.N;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kNpWarps; ++w) v += part[((size_t)w * a.n + b) * kNpCols + c];
+        red[b * kNpCols + c] = v;
+    }
+    NP_STAMP();
+    cluster.sync();
+    NP_STAMP();
+    constexpr int kPer = kNpCols / kNpCluster;
+    if (tid < a.n * kPer) {
+        const int b = tid / kPer, c = rank * kPer + (tid - b * kPer);
+        if (c < a.N) {
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < kNpCluster; ++q) v += cluster.map_shared_rank(red, q)[b * kNpCols + c];
+            for (int p = 0; p < 3; ++p)
+                if (a.bias[p] != nullptr) v += __ldg(a.bias[p] + c);
+            if (a.act_tanh) v = tanhf(v);
+            a.out[(long long)b * a.ldo + c] = v;
+        }
+    }
+    NP_STAMP();
+    cluster.sync();                                               // remote reads done before any CTA exits
+    NP_STAMP();
+#ifdef NARROW_TRACE
+    if (tid == 0 && rank == 0) printf("[narrow] stage_w +%llu | xs +%llu | main +%llu | reduce +%llu | csync +%llu | tail +%llu | csync +%llu ns\n", ts[1]-ts[0], ts[2]-ts[1], ts[3]-ts[2], ts[4]-ts[3], ts[5]-ts[4], ts[6]-ts[5], ts[7]-ts[6]);
+#endif
+#undef NP_STAMP
+}
+
+size_t narrow_proj_smem(const NarrowProj& a) {
+    const int rows = cdiv(a.K[0] + a.K[1] + a.K[2], kNpCluster);
+    size_t wsf = (size_t)rows * a.N;                              // the weight stage doubles as the per-warp partial sums
+    if (wsf < (size_t)kNpWarps * a.n * kNpCols) wsf = (size_t)kNpWarps * a.n * kNpCols;
+    return (wsf + (size_t)rows * kNpMaxRows + (size_t)a.n * kNpCols) * sizeof(float);
+}
+int g_np_dyn_limit = 48 * 1024;
+
 }  // namespace
+
+int narrow_proj_setup(const nats_ctx* ctx) {
+    cudaFuncAttributes fa;
+    NATS_CUDA_OK(cudaFuncGetAttributes(&fa, narrow_proj_kernel));
+    const int lim = ctx->max_smem_optin - (int)fa.sharedSizeBytes;
+    NATS_CUDA_OK(cudaFuncSetAttribute(narrow_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    g_np_dyn_limit = lim;
+    return 0;
+}
+
+bool narrow_proj_eligible(const NarrowProj& a) {
+    static const int off = [] { const char* e = getenv("NATS_NARROW_PROJ"); return e && atoi(e) == 0; }();
+    if (off || a.n < 1 || a.n > kNpMaxRows || a.N < 4 || a.N > kNpCols || (a.N & 3)) return false;
+    for (int p = 0; p < 3; ++p)                                    // 16-byte weight rows
+        if (a.K[p] > 0 && ((a.ldw[p] & 3) || (reinterpret_cast<uintptr_t>(a.W[p]) & 15))) return false;
+    return a.K[0] + a.K[1] + a.K[2] >= 1 && narrow_proj_smem(a) <= (size_t)g_np_dyn_limit;
+}
+
+int narrow_proj(cudaStream_t st, const NarrowProj& a) {
+    NATS_REQUIRE(narrow_proj_eligible(a), "narrow_proj shape");
+    const int Kt = a.K[0] + a.K[1] + a.K[2];
+    const int rows = cdiv(Kt, kNpCluster);
+    ProfScope ps(st, K_ELEMWISE, 2.0 * a.n * Kt * a.N, 4.0 * ((double)Kt * a.N + (double)a.n * Kt + (double)a.n * a.N));
+    NATS_CUDA_OK(launch_pdl(narrow_proj_kernel, dim3(kNpCluster), dim3(kNpThreads), narrow_proj_smem(a), st, a, rows));
+    return 0;
+}
 
 int nll_rows(cudaStream_t st, const float* logits, int rows, int V, const int64_t* y, const float* ymask, float* lse,
              float* rowcost) {

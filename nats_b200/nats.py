@@ -970,8 +970,24 @@ def build_sampler(tparams, options, trng=None):
         eng.launches += 1
         counter[0] += 1
 
+    def bind_next(y_d, ctx_d, pctx_d, st_d, ac_d, aa_d, Tx, n, outs):
+        """next_device with every pointer argument converted ONCE: a zero-argument callable for the beam-search loop (the
+        tensors must stay alive and in place, which the caller's ping-pong buffers do)"""
+        ws, nbytes = ws_for(Tx, n)
+        args = (eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(y_d), _ptr(ctx_d), C, 0, _ptr(pctx_d), A, 0,
+                _ptr(st_d), _ptr(ac_d), _ptr(aa_d), Tx, n, seed, 0, _ptr(ws), nbytes) + tuple(_ptr(o) for o in outs)
+        fn = eng.lib.nats_sampler_next
+
+        def call():
+            rc = fn(*args)
+            if rc != 0:
+                _lib.check(rc, 'nats_sampler_next')
+        call.keep = (ws, y_d, ctx_d, pctx_d, st_d, ac_d, aa_d, outs)
+        return call
+
     f_next.last_device = None
     f_next.engine = eng
+    f_next.bind_next = bind_next
     f_next.topk = topk
     f_next.next_device = next_device
     f_next.dims = (V, W, D, A)
@@ -1081,50 +1097,49 @@ def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_fac
     top_p, top_i = torch.empty((k, k), **f32), torch.empty((k, k), **i32)
     pen = torch.zeros((3 * k,), **f32)
     scratch = torch.zeros((3 * k * maxlen + 16,), **f32)
-    flags = [(torch.zeros(8, dtype=torch.int32).pin_memory(), torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
-    side = getattr(eng, '_flag_stream', None)                 # the flag copy must not sit between two steps' kernels
-    if side is None:
-        side = eng._flag_stream = torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream(dev)
+    # `done` reaches the host without a copy: nats_beam_select mirrors the counters into pinned host memory, the loop looks at
+    # them two steps late (after that step's event), so the GPU queue never drains.  All pointer arguments are converted
+    # once, per ping-pong parity: the loop body is five C calls on prebuilt tuples.
+    host_cnt = torch.zeros(8, dtype=torch.int32).pin_memory()
+    host_np = host_cnt.numpy()
+    events = [torch.cuda.Event() for _ in range(2)]
+    P, cf = _ptr, ctypes.c_float
+    stream = eng.stream()
+    step_next = [f_next.bind_next(next_w, ctx_d, pctx_d, state[c], acc_ctx[c], acc_alpha[c], Tx, k, outs) for c in (0, 1)]
+    pen_head = [(eng.ctx, stream, P(hist_alpha[c]), P(hist_ctx[c]), P(hist_state[c]), maxlen) for c in (0, 1)]
+    pen_tail = (k, Tx, C, D, P(outs[3]), P(outs[4]), P(outs[2]), cf(kl_factor), cf(ctx_factor), cf(state_factor), P(scratch), P(pen))
+    topk_args = (eng.ctx, stream, P(outs[0]), k, V, k, 0 if use_unk else 1, P(top_p), P(top_i))
+    sel_head = (eng.ctx, stream, P(top_p), P(top_i))
+    sel_tail = (P(counters), P(scores), P(tokens), P(parents), P(next_w), P(out_tokens), P(out_len), P(out_score), P(fin_parent),
+                P(host_cnt))
+    pen_ptr, no_ptr = P(pen), P(None)
+    adv_head = (eng.ctx, stream, P(parents), P(fin_parent), P(counters), k, maxlen)
+    adv_tail = [(Tx, C, D, P(outs[2]), P(state[c ^ 1]), P(outs[5]), P(acc_ctx[c ^ 1]), P(outs[6]), P(acc_alpha[c ^ 1]),
+                 P(outs[3]), P(outs[4]), P(outs[2]), P(hist_alpha[c]), P(hist_alpha[c ^ 1]), P(hist_ctx[c]), P(hist_ctx[c ^ 1]),
+                 P(hist_state[c]), P(hist_state[c ^ 1]), P(out_alpha)) for c in (0, 1)]
+    check = _lib.check
     for ii in range(maxlen):
         cur = ii & 1
-        f_next.next_device(next_w, ctx_d, pctx_d, state[cur], acc_ctx[cur], acc_alpha[cur], Tx, k, outs)
+        if ii >= 2:
+            events[cur].synchronize()                         # step ii-2 is through: its counters are in host memory
+            if host_np[2] != 0:
+                break
+        step_next[cur]()
         use_pen = distract and ii > 0
         if use_pen:
-            _lib.check(lib.nats_beam_distraction_scores(
-                eng.ctx, eng.stream(), _ptr(hist_alpha[cur]), _ptr(hist_ctx[cur]), _ptr(hist_state[cur]), maxlen, ii, k, Tx, C, D,
-                _ptr(outs[3]), _ptr(outs[4]), _ptr(outs[2]), ctypes.c_float(kl_factor), ctypes.c_float(ctx_factor),
-                ctypes.c_float(state_factor), _ptr(scratch), _ptr(pen)), 'nats_beam_distraction_scores')
+            check(lib.nats_beam_distraction_scores(*pen_head[cur], ii, *pen_tail), 'nats_beam_distraction_scores')
             if _trace is not None:
                 live_now = int(counters[0].item())
                 _trace.append(dict(ii=ii, pen=pen.cpu().numpy().reshape(3, k)[:, :live_now].copy()))
-        _lib.check(lib.nats_beam_topk(eng.ctx, eng.stream(), _ptr(outs[0]), k, V, k, 0 if use_unk else 1, _ptr(top_p),
-                                      _ptr(top_i)), 'nats_beam_topk')
-        _lib.check(lib.nats_beam_select(eng.ctx, eng.stream(), _ptr(top_p), _ptr(top_i), _ptr(pen) if use_pen else None, k, maxlen,
-                                        ii, _ptr(counters), _ptr(scores), _ptr(tokens), _ptr(parents), _ptr(next_w),
-                                        _ptr(out_tokens), _ptr(out_len), _ptr(out_score), _ptr(fin_parent)), 'nats_beam_select')
-        _lib.check(lib.nats_beam_advance(
-            eng.ctx, eng.stream(), _ptr(parents), _ptr(fin_parent), _ptr(counters), k, maxlen, ii, Tx, C, D,
-            _ptr(outs[2]), _ptr(state[cur ^ 1]), _ptr(outs[5]), _ptr(acc_ctx[cur ^ 1]), _ptr(outs[6]), _ptr(acc_alpha[cur ^ 1]),
-            _ptr(outs[3]), _ptr(outs[4]), _ptr(outs[2]), _ptr(hist_alpha[cur]), _ptr(hist_alpha[cur ^ 1]),
-            _ptr(hist_ctx[cur]), _ptr(hist_ctx[cur ^ 1]), _ptr(hist_state[cur]), _ptr(hist_state[cur ^ 1]), _ptr(out_alpha)),
-            'nats_beam_advance')
-        eng.launches += 4
-        buf, sel_ev, ev = flags[cur]
-        sel_ev.record(main)
-        side.wait_event(sel_ev)
-        with torch.cuda.stream(side):                         # `done` only ever goes 0 -> 1: a later step's value is fine
-            buf.copy_(counters, non_blocking=True)
-            ev.record(side)
-        if ii > 0:                                            # the flag of the PREVIOUS step: its copy has long completed
-            pbuf, _, pev = flags[cur ^ 1]
-            pev.synchronize()
-            if int(pbuf[2]) != 0:
-                break
+        check(lib.nats_beam_topk(*topk_args), 'nats_beam_topk')
+        check(lib.nats_beam_select(*sel_head, pen_ptr if use_pen else no_ptr, k, maxlen, ii, *sel_tail), 'nats_beam_select')
+        check(lib.nats_beam_advance(*adv_head, ii, *adv_tail[cur]), 'nats_beam_advance')
+        eng.launches += 5
+        events[cur].record()
     torch.cuda.synchronize(dev)
     cnt = counters.cpu().numpy()
     live_k, n_fin = int(cnt[0]), int(cnt[3])
-    # with the one-step-late flag a step may have run after `done`: nats_beam_select leaves everything untouched then
+    # with the late flag up to two steps may have run after `done`: nats_beam_select leaves everything untouched then
     fin_tok, fin_len, fin_sc = out_tokens.cpu().numpy(), out_len.cpu().numpy(), out_score.cpu().numpy()
     fin_al = out_alpha.cpu().numpy()
     sample, sample_score, sample_dec_alphas = [], [], []

@@ -181,6 +181,9 @@ SWITCHES = [
     {'NATS_TC': '1'},                     # tcgen05 with software loaders (no TMA)
     {'NATS_TS': '0'},                     # skinny products from shared memory instead of tensor memory
     {'NATS_PDL': '0'},                    # no programmatic dependent launch
+    # beam-search kernels: one CTA per row / per (row, slice) and library GEMMs instead of the 8-CTA cluster kernels
+    {'NATS_TOPK_SIMPLE': '1', 'NATS_SOFTMAX_SIMPLE': '1', 'NATS_ATT_BCAST': '0', 'NATS_NARROW_PROJ': '0'},
+    {'NATS_DEVICE_BEAM': '0'},            # beam bookkeeping on the host (the reference's loop) instead of on the device
 ]
 
 
@@ -191,6 +194,6 @@ def test_kernel_switches_keep_parity(env):
     e = dict(os.environ)
     e.update(env)
     r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', '-m', 'gpu', 'tests/test_gpu_parity.py', '-k',
-                        'cost_and_grads or real_dims or sampler_matches'], cwd=ROOT, env=e, capture_output=True, text=True,
+                        'cost_and_grads or real_dims or sampler_matches or sampler_batched or beam_search or topk'], cwd=ROOT, env=e, capture_output=True, text=True,
                        timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -31,3 +31,14 @@ for st, en, name in evs:
 print('wall %.2f ms (profiled), GPU busy %.2f ms, %d kernels, %.1f kernels/step, busy per step %.1f us' % (wall * 1e3, busy / 1e3, len(evs), len(evs) / steps, busy / steps))
 for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:24]:
     print('  %-50s %8.1f us  %5d launches  %6.2f us/launch' % (k, v[0], v[1], v[0] / v[1]))
+# timeline of one step in the middle: start offset, duration, gap to the previous end
+sel = [i for i, e in enumerate(evs) if 'gather_rows' in e[2]]
+if len(sel) > 22:
+    lo, hi = sel[20], sel[21]
+    t0 = evs[lo][0]; prev_end = t0
+    print('--- timeline of one beam step (us): start  dur  gap_after_prev_end  name')
+    for st, en, name in evs[lo:hi]:
+        k = re.sub(r'\(anonymous namespace\)::|nats::|void ', '', name).split('(')[0][:44]
+        print('  %8.1f %7.1f %7.1f  %s' % (st - t0, en - st, st - prev_end, k))
+        prev_end = max(prev_end, en)
+    print('  step span %.1f us' % (evs[hi][0] - t0))
