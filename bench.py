@@ -381,7 +381,7 @@ def region_r1(eng, _lib, graph, plan, tparams, w, tokens_per_step, n=10):
             'kernels': rows, 'how': 'one CUDA graph, CUDA events, %d replays' % n}
 
 
-def beam_run(nats, tparams, opts, w, steps, warm=True):
+def beam_run(nats, tparams, opts, w, steps, warm=True, kernels=False):
     """gen_sample at beam 10 with all three penalties; the EOS logit is pushed down so that all 10 hypotheses stay alive."""
     import torch
     rng = np.random.RandomState(4321)
@@ -406,9 +406,25 @@ def beam_run(nats, tparams, opts, w, steps, warm=True):
     finally:
         tparams['ff_logit_b'].set_value(bsave)
     live = 1 + 10 * (steps - 1)
-    return {'ms_per_step': (dt - t_init) / steps * 1e3, 'f_init_ms': t_init * 1e3, 'steps': steps, 'sentence_ms': dt * 1e3,
-            'hyp_tokens_per_s': live / max(dt - t_init, 1e-9),
-            'how': 'gen_sample wall clock (host bookkeeping included) minus one f_init; beam 10, src_len %d, kl=ctx=state=1' % (w['Tx'] - 1)}
+    out = {'ms_per_step': (dt - t_init) / steps * 1e3, 'f_init_ms': t_init * 1e3, 'steps': steps, 'sentence_ms': dt * 1e3,
+           'hyp_tokens_per_s': live / max(dt - t_init, 1e-9),
+           'how': 'gen_sample wall clock (host bookkeeping included) minus one f_init; beam 10, src_len %d, kl=ctx=state=1' % (w['Tx'] - 1)}
+    if kernels:
+        # the same sentence under the CUPTI activity trace: launches and exclusive device time per kernel
+        tparams['ff_logit_b'].set_value(bmod)
+        try:
+            rows = kernel_table(torch, lambda: nats.gen_sample(tparams, f_init, f_next, x, opts, None, 10, steps, False, False, True,
+                                                               1.0, 1.0, 1.0), steps=1)
+        finally:
+            tparams['ff_logit_b'].set_value(bsave)
+        launches = sum(v[2] for k_, v in rows.items() if 'memcpy' not in k_.lower() and 'memset' not in k_.lower())
+        busy = sum(v[0] for v in rows.values())
+        top = sorted(rows.items(), key=lambda kv: -kv[1][0])[:12]
+        out['kernels'] = {'launches_per_sentence': int(launches), 'launches_per_step': launches / float(steps),
+                          'gpu_busy_us_per_step_incl_f_init': busy / steps,
+                          'top': [{'kernel': k_.replace('(anonymous namespace)::', '').replace('nats::', '').replace('void ', '').split('(')[0][:60],
+                                   'excl_us': round(v[0], 1), 'launches': v[2]} for k_, v in top]}
+    return out
 
 
 def main():
@@ -485,15 +501,20 @@ def main():
         K = max(args.steps, 4)
         clk = ClockSampler(local)
         t0 = time.time()
-        r = beam_run(nats, tparams, opts, w, K)
+        r = beam_run(nats, tparams, opts, w, K, kernels=not args.no_kernels)
         full = beam_run(nats, tparams, opts, w, 100, warm=False)
         clocks = clk.stop(t0, time.time())
+        Tx5, k5 = w['Tx'], 10
+        d2h_sentence = 2 * k5 * K * Tx5 * 4 + 2 * k5 * K * 4 + 3 * k5 * 4 + 32     # attention histories (live + retired), tokens, scores, counters
         line = {'metric': METRIC, 'value': r['hyp_tokens_per_s'], 'unit': 'tokens/s', 'n_gpus': 1, 'steps': K, 'warmup': 4,
                 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks,
-                'e2e': {'value': r['hyp_tokens_per_s'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 8 * 10,
-                        'd2h_bytes_per_step': 4 * 10 * 10 * 2 + 3 * 4 * 10, 'note': 'gen_sample is the public API: host loop included'},
-                'beam': r, 'full_sentence_100_steps': full, 'gpu_launches': None}
+                'e2e': {'value': r['hyp_tokens_per_s'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 8.0 * Tx5 / K,
+                        'd2h_bytes_per_step': d2h_sentence / float(K),
+                        'note': 'gen_sample is the public API: host loop included; the source sentence goes up once per '
+                                'sentence, the search state stays on the device, results come back once at the end'},
+                'beam': r, 'full_sentence_100_steps': full,
+                'gpu_launches': (r.get('kernels') or {}).get('launches_per_sentence')}
         if not args.no_cpu_baseline:
             c = cpu_beam_steps(w, steps=6)
             line['cpu_baseline'] = {'value': c['value'], 'unit': 'tokens/s', 'cores': c['cores'], 'kind': 'port',
@@ -683,11 +704,19 @@ def roofline_of(cls, w, step_ms):
     us = k['us_per_launch']
     base = {'kernel': name, 'share_of_step': k['ms_per_step'] / step_ms, 'us_per_launch': us, 'peak_source': src,
             'duration_source': 'CUPTI activity trace of the replayed graph step'}
+    traffic = None                                            # dram bytes per launch from the committed ncu --set full capture
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_traffic.json')) as f:
+            t = json.load(f).get(name)
+        if t and (t.get('Tx'), t.get('B'), t.get('dim')) == (w['Tx'], w['B'], w['dim']):
+            traffic = t['dram_bytes_per_launch']
+    except (OSError, ValueError, KeyError):
+        pass
     if name.startswith('enc_tc'):
         flops = 2.0 * 2 * (Tx - 1) * B * D * 3 * D            # both directions, fp32-equivalent (each is 3 tf32 products)
         ach = flops / (us * 1e-6) / 1e12
         base.update({'bound': 'tensor', 'achieved': ach, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach / tf,
-                     'algo_flops_per_launch': flops, 'traffic': None,
+                     'algo_flops_per_launch': flops, 'traffic': traffic,
                      'limiter': 'inter-SM dependency latency: 2 L2 exchange hops per recurrent step (K partials, then h_t / dG_t); '
                                 'the tensor pipe itself is busy ~1/3 of the step (84 tcgen05 MMAs of 3xTF32 per CTA and step)',
                      'us_per_recurrent_step': us / Tx})

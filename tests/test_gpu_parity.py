@@ -273,6 +273,38 @@ def test_beam_search_matches_oracle_and_golden(N):
     assert list(map(int, s1)) == list(map(int, s2))
 
 
+@pytest.mark.parametrize('k', [12, 20, 32])
+@pytest.mark.parametrize('model', ['golden', 'w8'])
+def test_beam_search_wide_beams(N, k, model):
+    """Beams of 12 / 20 / 32 rows: 12 still runs the few-row cluster kernels (<= 16 rows), 20 and 32 take the general
+    attention / library-GEMM paths under the same device-resident bookkeeping (beam <= 32); distraction on, early EOS
+    retirements included.  'w8' has dim_word = 8 (a multiple of 4: the fused readout projection is eligible), 'golden' has
+    dim_word = 6 (it is not).  Same tokens and scores as the oracle's literal restatement of nats.py:951-1066."""
+    if model == 'golden':
+        z = np.load(os.path.join(GOLD, 'beam_toy.npz'))
+        zt = np.load(os.path.join(GOLD, 'train_toy.npz'))
+        V, W, D, A = [int(v) for v in zt['opt_dims']]
+        opts = toy_options(D=D, W=W, A=A, V=V)
+        names = list(O.init_params(opts).keys())
+        P32 = O.cast_params(O.OrderedDict((kk, zt['p_' + kk]) for kk in names), 'float32')
+        x = z['x']
+    else:
+        opts = toy_options(D=32, W=8, A=12, V=120)
+        P32 = O.cast_params(toy_params(opts), 'float32')
+        x = np.concatenate([np.random.RandomState(7).randint(2, 120, size=23), [0]]).astype('int64')[:, None]
+    tparams = N.init_tparams(P32)
+    f_init, f_next = N.build_sampler(tparams, opts)
+    fi = lambda x_: O.f_init(P32, x_)
+    fn = lambda y_, c_, s_, ac_, aa_: O.f_next(P32, y_, c_, s_.astype('float32'), ac_.astype('float32'),
+                                               aa_.astype('float32'))
+    kw = dict(k=k, maxlen=8, stochastic=False, use_unk=True, kl_factor=0.5, ctx_factor=0.5, state_factor=0.5)
+    ref_s, ref_sc, _ = O.gen_sample(fi, fn, x, **kw)
+    got_s, got_sc, got_al = N.gen_sample(tparams, f_init, f_next, x, opts, **kw)
+    assert [list(map(int, s)) for s in got_s] == [list(map(int, s)) for s in ref_s]
+    np.testing.assert_allclose(np.array(got_sc, 'float64'), np.array(ref_sc, 'float64'), rtol=5e-4)
+    assert all(len(a) == len(s) for a, s in zip(got_al, got_s))
+
+
 def test_beam_topk_matches_numpy(N):
     """nats_beam_topk: per row the k largest probabilities, descending, ties by ascending index, entry 1 -> 1e-20
     when use_unk is off (nats.py:975) -- the selection that replaces the host argsort of nats.py:997-999."""
