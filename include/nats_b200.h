@@ -219,6 +219,36 @@ int nats_beam_advance(nats_ctx_t* ctx, void* stream, const int32_t* parents, con
                       const float* hist_alpha_src, float* hist_alpha_dst, const float* hist_ctx_src, float* hist_ctx_dst,
                       const float* hist_state_src, float* hist_state_dst, float* out_alpha);
 
+/* One beam-search step in ONE call (what nats.py:957-1066 does per iteration of `for ii in xrange(maxlen)`):
+ * nats_sampler_next on k rows of one source (zero batch stride, no multinomial draw) -> for step > 0 with a distraction
+ * factor on, nats_beam_distraction_scores -> nats_beam_topk (K = k) -> nats_beam_select -> nats_beam_advance, all on
+ * `stream`.  The struct carries the arguments of those five calls for one ping-pong parity (`*_in` buffers are read,
+ * `*_out` / `*_next` written; the caller swaps them every step); hist_ctx_* / hist_state_* / pen / scratch are NULL when
+ * all three factors are 0.  Exists because five foreign-function calls per step cost the host more than the step costs
+ * the GPU. */
+typedef struct nats_beam_step {
+    const float* params;                 /* flat parameter buffer */
+    const int64_t* next_w;               /* [k] previous words (-1 = BOS); nats_beam_select writes the next ones here */
+    const float* ctx; const float* pctx; /* [Tx, 2*dim], [Tx, dim_att] of the ONE source sentence */
+    int32_t Tx, k, maxlen, use_unk;
+    void* ws; int64_t ws_bytes;          /* nats_sampler_workspace_bytes(dims, Tx, k) */
+    /* f_next: state in, outputs */
+    const float* state_in; const float* acc_ctx_in; const float* acc_alpha_in;
+    float* probs; float* state_out; float* alphaT; float* ctxs; float* acc_ctx_out; float* acc_alpha_out;
+    /* distraction penalties (nats.py:981-999) */
+    float kl_factor, ctx_factor, state_factor;
+    const float* hist_alpha_in; const float* hist_ctx_in; const float* hist_state_in;
+    float* scratch; float* pen;
+    /* selection + bookkeeping */
+    float* top_p; int32_t* top_i;
+    int32_t* counters; float* scores; int32_t* tokens; int32_t* parents; int32_t* fin_parent;
+    int32_t* out_tokens; int32_t* out_len; float* out_score; float* out_alpha; int32_t* host_counters;
+    /* rows of the next step */
+    float* state_next; float* acc_ctx_next; float* acc_alpha_next;
+    float* hist_alpha_out; float* hist_ctx_out; float* hist_state_out;
+} nats_beam_step_t;
+int nats_beam_step(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const nats_beam_step_t* a, int step);
+
 /* ---------------------------------------------------------------- diagnostics ------------------- */
 /* The library's internal GEMM engine, exposed for the parity tests: C = op(A).op(B) (+bias) (+C), row-major,
  * path 0 = exact-fp32 FFMA kernels, path 1 = tcgen05 3xTF32 kernel with software loaders, path 2 = tcgen05 3xTF32

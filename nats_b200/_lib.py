@@ -24,6 +24,20 @@ class ParamView(Structure):
 
 _P = c_void_p     # device pointers travel as integers (tensor.data_ptr())
 
+
+class BeamStep(Structure):
+    """nats_beam_step_t of include/nats_b200.h, field for field"""
+    _fields_ = ([('params', _P), ('next_w', _P), ('ctx', _P), ('pctx', _P),
+                 ('Tx', c_int32), ('k', c_int32), ('maxlen', c_int32), ('use_unk', c_int32),
+                 ('ws', _P), ('ws_bytes', c_int64)] +
+                [(n, _P) for n in ('state_in', 'acc_ctx_in', 'acc_alpha_in', 'probs', 'state_out', 'alphaT', 'ctxs',
+                                   'acc_ctx_out', 'acc_alpha_out')] +
+                [('kl_factor', c_float), ('ctx_factor', c_float), ('state_factor', c_float)] +
+                [(n, _P) for n in ('hist_alpha_in', 'hist_ctx_in', 'hist_state_in', 'scratch', 'pen', 'top_p', 'top_i',
+                                   'counters', 'scores', 'tokens', 'parents', 'fin_parent', 'out_tokens', 'out_len',
+                                   'out_score', 'out_alpha', 'host_counters', 'state_next', 'acc_ctx_next',
+                                   'acc_alpha_next', 'hist_alpha_out', 'hist_ctx_out', 'hist_state_out')])
+
 # name -> (restype, argtypes); mirrors include/nats_b200.h one to one (checked by tests/test_abi.py)
 SIGNATURES = {
     'nats_last_error': (c_char_p, []),
@@ -66,6 +80,7 @@ SIGNATURES = {
     'nats_beam_reorder_append': (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int]),
     'nats_beam_select': (c_int, [c_void_p, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'nats_beam_advance': (c_int, [c_void_p, _P] + [_P] * 3 + [c_int] * 6 + [_P] * 16),
+    'nats_beam_step': (c_int, [c_void_p, _P, POINTER(Dims), POINTER(BeamStep), c_int]),
     'nats_debug_gemm': (c_int, [c_void_p, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, c_int,
                                 _P, c_int, c_int, c_int, c_int64, c_int64, c_int64]),
     'nats_profile_enable': (c_int, [c_void_p, c_int]),

@@ -540,4 +540,30 @@ int nats_beam_advance(nats_ctx_t* ctx, void* stream, const int32_t* parents, con
                         hist_alpha_src, hist_alpha_dst, hist_ctx_src, hist_ctx_dst, hist_state_src, hist_state_dst, out_alpha);
 }
 
+int nats_beam_step(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const nats_beam_step_t* a, int step) {
+    NATS_REQUIRE(ctx && dims && a, "null argument");
+    NATS_REQUIRE(a->k >= 1 && a->maxlen >= 1 && step >= 0 && step < a->maxlen, "beam step shape");
+    const int D = dims->dim, C = 2 * D, A = dims->dim_att, V = dims->n_words, k = a->k, Tx = a->Tx;
+    NATS_TRY(nats_sampler_next(ctx, stream, dims, a->params, a->next_w, a->ctx, C, 0, a->pctx, A, 0, a->state_in, a->acc_ctx_in,
+                               a->acc_alpha_in, Tx, k, 0, 0, a->ws, a->ws_bytes, a->probs, nullptr, a->state_out, a->alphaT,
+                               a->ctxs, a->acc_ctx_out, a->acc_alpha_out));
+    const bool distract = a->kl_factor > 0.f || a->ctx_factor > 0.f || a->state_factor > 0.f;
+    const bool use_pen = distract && step > 0;
+    if (use_pen) {
+        NATS_REQUIRE(a->hist_ctx_in && a->hist_state_in && a->scratch && a->pen, "distraction buffers");
+        NATS_TRY(nats_beam_distraction_scores(ctx, stream, a->hist_alpha_in, a->hist_ctx_in, a->hist_state_in, a->maxlen, step, k,
+                                              Tx, C, D, a->alphaT, a->ctxs, a->state_out, a->kl_factor, a->ctx_factor,
+                                              a->state_factor, a->scratch, a->pen));
+    }
+    NATS_TRY(nats_beam_topk(ctx, stream, a->probs, k, V, k, a->use_unk ? 0 : 1, a->top_p, a->top_i));
+    NATS_TRY(nats_beam_select(ctx, stream, a->top_p, a->top_i, use_pen ? a->pen : nullptr, k, a->maxlen, step, a->counters,
+                              a->scores, a->tokens, a->parents, const_cast<int64_t*>(a->next_w), a->out_tokens, a->out_len,
+                              a->out_score, a->fin_parent, a->host_counters));
+    NATS_TRY(nats_beam_advance(ctx, stream, a->parents, a->fin_parent, a->counters, k, a->maxlen, step, Tx, C, D, a->state_out,
+                               a->state_next, a->acc_ctx_out, a->acc_ctx_next, a->acc_alpha_out, a->acc_alpha_next, a->alphaT,
+                               a->ctxs, a->state_out, a->hist_alpha_in, a->hist_alpha_out, distract ? a->hist_ctx_in : nullptr,
+                               a->hist_ctx_out, a->hist_state_in, a->hist_state_out, a->out_alpha));
+    return 0;
+}
+
 }  // extern "C"

@@ -988,6 +988,7 @@ def build_sampler(tparams, options, trng=None):
     f_next.last_device = None
     f_next.engine = eng
     f_next.bind_next = bind_next
+    f_next.beam_env = (ws_for, tparams, dims)      # what nats_beam_step needs besides the search buffers
     f_next.topk = topk
     f_next.next_device = next_device
     f_next.dims = (V, W, D, A)
@@ -1118,12 +1119,45 @@ def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_fac
                  P(outs[3]), P(outs[4]), P(outs[2]), P(hist_alpha[c]), P(hist_alpha[c ^ 1]), P(hist_ctx[c]), P(hist_ctx[c ^ 1]),
                  P(hist_state[c]), P(hist_state[c ^ 1]), P(out_alpha)) for c in (0, 1)]
     check = _lib.check
+    # without a trace the whole step is ONE foreign call (nats_beam_step) on a prebuilt argument struct per parity
+    ws_for, tp_, dims_ = f_next.beam_env
+    ws_t, ws_bytes = ws_for(Tx, k)
+    one_call = []
+    for c in (0, 1):
+        a = _lib.BeamStep()
+        a.params, a.next_w, a.ctx, a.pctx = tp_.flat.data_ptr(), next_w.data_ptr(), ctx_d.data_ptr(), pctx_d.data_ptr()
+        a.Tx, a.k, a.maxlen, a.use_unk = Tx, k, maxlen, 1 if use_unk else 0
+        a.ws, a.ws_bytes = ws_t.data_ptr(), ws_bytes
+        a.state_in, a.acc_ctx_in, a.acc_alpha_in = state[c].data_ptr(), acc_ctx[c].data_ptr(), acc_alpha[c].data_ptr()
+        a.probs, a.state_out, a.alphaT, a.ctxs = outs[0].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), outs[4].data_ptr()
+        a.acc_ctx_out, a.acc_alpha_out = outs[5].data_ptr(), outs[6].data_ptr()
+        a.kl_factor, a.ctx_factor, a.state_factor = kl_factor, ctx_factor, state_factor
+        a.hist_alpha_in = hist_alpha[c].data_ptr()
+        a.hist_ctx_in = hist_ctx[c].data_ptr() if distract else None
+        a.hist_state_in = hist_state[c].data_ptr() if distract else None
+        a.scratch, a.pen, a.top_p, a.top_i = scratch.data_ptr(), pen.data_ptr(), top_p.data_ptr(), top_i.data_ptr()
+        a.counters, a.scores, a.tokens, a.parents = counters.data_ptr(), scores.data_ptr(), tokens.data_ptr(), parents.data_ptr()
+        a.fin_parent, a.out_tokens, a.out_len = fin_parent.data_ptr(), out_tokens.data_ptr(), out_len.data_ptr()
+        a.out_score, a.out_alpha, a.host_counters = out_score.data_ptr(), out_alpha.data_ptr(), host_cnt.data_ptr()
+        a.state_next, a.acc_ctx_next, a.acc_alpha_next = state[c ^ 1].data_ptr(), acc_ctx[c ^ 1].data_ptr(), acc_alpha[c ^ 1].data_ptr()
+        a.hist_alpha_out = hist_alpha[c ^ 1].data_ptr()
+        a.hist_ctx_out = hist_ctx[c ^ 1].data_ptr() if distract else None
+        a.hist_state_out = hist_state[c ^ 1].data_ptr() if distract else None
+        one_call.append((eng.ctx, stream, ctypes.byref(dims_), ctypes.byref(a)))
+    beam_step = lib.nats_beam_step
     for ii in range(maxlen):
         cur = ii & 1
         if ii >= 2:
             events[cur].synchronize()                         # step ii-2 is through: its counters are in host memory
             if host_np[2] != 0:
                 break
+        if _trace is None:
+            rc = beam_step(*one_call[cur], ii)
+            if rc != 0:
+                check(rc, 'nats_beam_step')
+            eng.launches += 1
+            events[cur].record()
+            continue
         step_next[cur]()
         use_pen = distract and ii > 0
         if use_pen:
