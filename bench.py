@@ -395,8 +395,10 @@ def beam_run(nats, tparams, opts, w, steps, warm=True, kernels=False):
         if warm:                                     # same maxlen as the timed run: buffers of that size, kernels loaded
             nats.gen_sample(tparams, f_init, f_next, x, opts, None, 10, steps, False, False, True, 1.0, 1.0, 1.0)
         torch.cuda.synchronize()
+        f_init.device(x)                              # the call gen_sample makes (device tensors, no host copies); warm
+        torch.cuda.synchronize()
         t1 = time.time()
-        f_init(x)
+        f_init.device(x)
         torch.cuda.synchronize()
         t_init = time.time() - t1
         t0 = time.time()
@@ -424,6 +426,39 @@ def beam_run(nats, tparams, opts, w, steps, warm=True, kernels=False):
                           'gpu_busy_us_per_step_incl_f_init': busy / steps,
                           'top': [{'kernel': k_.replace('(anonymous namespace)::', '').replace('nats::', '').replace('void ', '').split('(')[0][:60],
                                    'excl_us': round(v[0], 1), 'launches': v[2]} for k_, v in top]}
+    return out
+
+
+def gen_throughput(nats, tparams, opts, w, n_sent=16, steps=25):
+    """What gen.py does per worker: a stream of source sentences, beam 10 each.  With f_init.prefetch the 16 encoders run
+    as ONE masked launch of the persistent kernel; without, one launch per sentence.  EOS is suppressed: every sentence
+    runs all `steps` steps (a summary-sized output)."""
+    import torch
+    rng = np.random.RandomState(99)
+    xs = [np.array(rng.randint(2, w['n_words'], size=(w['Tx'] - 1 - 7 * i,)).tolist() + [0], dtype='int64') for i in range(n_sent)]
+    f_init, f_next = nats.build_sampler(tparams, opts, None)
+    bsave = tparams['ff_logit_b'].get_value()
+    bmod = bsave.copy()
+    bmod[0] = -1e9
+    tparams['ff_logit_b'].set_value(bmod)
+    out = {}
+    try:
+        for mode in ('one_f_init_per_sentence', 'prefetch_16'):
+            for rep in range(2):                              # first pass warms buffers and kernels
+                torch.cuda.synchronize()
+                t0 = time.time()
+                if mode == 'prefetch_16':
+                    f_init.prefetch(xs)
+                for x in xs:
+                    nats.gen_sample(tparams, f_init, f_next, x[:, None], opts, None, 10, steps, False, False, True, 1.0, 1.0, 1.0)
+                torch.cuda.synchronize()
+                dt = time.time() - t0
+            out[mode] = {'sentences_per_s': n_sent / dt, 'ms_per_sentence': dt / n_sent * 1e3,
+                         'hyp_tokens_per_s': n_sent * (1 + 10 * (steps - 1)) / dt}
+    finally:
+        tparams['ff_logit_b'].set_value(bsave)
+    out['how'] = '%d sentences of src_len %d..%d, beam 10, %d steps each, kl=ctx=state=1; wall clock incl. f_init and result copies' % (
+        n_sent, w['Tx'] - 1 - 7 * (n_sent - 1), w['Tx'] - 1, steps)
     return out
 
 
@@ -513,7 +548,7 @@ def main():
                         'd2h_bytes_per_step': d2h_sentence / float(K),
                         'note': 'gen_sample is the public API: host loop included; the source sentence goes up once per '
                                 'sentence, the search state stays on the device, results come back once at the end'},
-                'beam': r, 'full_sentence_100_steps': full,
+                'beam': r, 'full_sentence_100_steps': full, 'gen_stream': gen_throughput(nats, tparams, opts, w),
                 'gpu_launches': (r.get('kernels') or {}).get('launches_per_sentence')}
         if not args.no_cpu_baseline:
             c = cpu_beam_steps(w, steps=6)

@@ -126,9 +126,12 @@ const float* nats_train_ws_view(const nats_dims_t* dims, int Tx, int Ty, int B, 
 int64_t nats_sampler_workspace_bytes(const nats_dims_t* dims, int Tx, int n);
 
 /* replaces: f_init (nats.py:789-817).  x [Tx,n] i64 -> init_state [n,D], ctx [Tx,n,C]; additionally returns
- * pctx [Tx,n,A] = ctx.Wc_att + b_att (nats.py:493-494) so that f_next need not recompute it every step. */
+ * pctx [Tx,n,A] = ctx.Wc_att + b_att (nats.py:493-494) so that f_next need not recompute it every step.
+ * x_mask [Tx,n] (NULL = the reference's f_init: no mask): encodes SEVERAL sentences of different lengths in one call,
+ * exactly as the training encoder does (nats.py:700-724, masked GRU steps, masked mean for init_state); rows t >= length
+ * of column i of ctx / pctx are then padding and must be cut by the caller. */
 int nats_sampler_init(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params,
-                      const int64_t* x, int Tx, int n, void* ws, int64_t ws_bytes,
+                      const int64_t* x, const float* x_mask, int Tx, int n, void* ws, int64_t ws_bytes,
                       float* init_state, float* ctx_out, float* pctx_out);
 
 /* replaces: f_next (nats.py:821-871) = embed (y<0 -> zeros) + one _step_slice (nats.py:498-572, mask == 1,

@@ -64,7 +64,7 @@ SIGNATURES = {
     'nats_encoder_bwd': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, _P]),
     'nats_train_ws_view': (c_void_p, [POINTER(Dims), c_int, c_int, c_int, _P, c_char_p]),
     'nats_sampler_workspace_bytes': (c_int64, [POINTER(Dims), c_int, c_int]),
-    'nats_sampler_init': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, c_int, c_int, _P, c_int64, _P, _P, _P]),
+    'nats_sampler_init': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, _P]),
     'nats_sampler_next': (c_int, [c_void_p, _P, POINTER(Dims), _P, _P, _P, c_int64, c_int64, _P, c_int64, c_int64,
                                   _P, _P, _P, c_int, c_int, c_uint64, c_uint64, _P, c_int64,
                                   _P, _P, _P, _P, _P, _P, _P]),

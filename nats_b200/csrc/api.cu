@@ -350,7 +350,8 @@ int64_t nats_sampler_workspace_bytes(const nats_dims_t* dims, int Tx, int n) {
 }
 
 int nats_sampler_init(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, const float* params, const int64_t* x,
-                      int Tx, int n, void* ws, int64_t ws_bytes, float* init_state, float* ctx_out, float* pctx_out) {
+                      const float* x_mask, int Tx, int n, void* ws, int64_t ws_bytes, float* init_state, float* ctx_out,
+                      float* pctx_out) {
     NATS_REQUIRE(ctx && ws && params && x && init_state && ctx_out, "null argument");
     NATS_TRY(check_dims(dims));
     NATS_REQUIRE(Tx >= 1 && n >= 1, "shape");
@@ -366,7 +367,7 @@ int nats_sampler_init(nats_ctx_t* ctx, void* stream, const nats_dims_t* dims, co
     e.gemm_scratch = w.gemm_scratch; e.gemm_scratch_floats = w.gemm_scratch_floats;
     e.enc_scratch = w.enc_scratch; e.enc_scratch_floats = w.enc_scratch_floats;
     e.enc_counters = w.enc_counters; e.enc_counter_ints = w.enc_counter_ints;
-    NATS_TRY(encoder_forward(ctx, st, *dims, params, x, nullptr, Tx, n, e));      // no masks (nats.py:801-804, 810)
+    NATS_TRY(encoder_forward(ctx, st, *dims, params, x, x_mask, Tx, n, e));       // NULL: no masks (nats.py:801-804, 810)
     if (pctx_out) {
         const ParamOff o = param_offsets(*dims);
         const int A = dims->dim_att, C = 2 * dims->dim;

@@ -22,6 +22,9 @@ def _load_pickle(path):
             return pkl.load(f, encoding='latin1')
 
 
+CHUNK = 16     # sentences encoded per f_init launch (and per queue item of a worker process)
+
+
 class _Translator(object):
     """one model replica: parameters from the checkpoint, sampler, beam search (gen.py:15-48)"""
 
@@ -33,6 +36,12 @@ class _Translator(object):
         self.f_init, self.f_next = nats.build_sampler(self.tparams, options, None)
         self.options, self.k, self.normalize = options, k, normalize
         self.factors = (kl_factor, ctx_factor, state_factor)
+
+    def prefetch(self, seqs):
+        """encode the next sentences in ONE encoder launch (f_init is most of a short summary's time); optional"""
+        pf = getattr(self.f_init, 'prefetch', None)
+        if pf is not None and self.k <= 32 and os.environ.get('NATS_DEVICE_BEAM', '1') != '0':
+            pf([numpy.array(s, dtype='int64') for s in seqs])
 
     def __call__(self, seq):
         kl, cf, sf = self.factors
@@ -58,10 +67,11 @@ def translate_model(queue, rqueue, pid, model, options, k, normalize, kl_factor,
         req = queue.get()
         if req is None:
             break
-        idx, x = req
-        print(pid, '-', idx)
-        seq, pos = tr(x)
-        rqueue.put((idx, seq, pos))
+        tr.prefetch([x for _, x in req])                       # a chunk of jobs: one encoder launch for all of them
+        for idx, x in req:
+            print(pid, '-', idx)
+            seq, pos = tr(x)
+            rqueue.put((idx, seq, pos))
 
 
 def main(model, dictionary, source_file, saveto, k=5, normalize=False, n_process=5, chr_level=False, kl_factor=0,
@@ -87,6 +97,8 @@ def main(model, dictionary, source_file, saveto, k=5, normalize=False, n_process
     if n_process <= 1:
         tr = _Translator(model, options, k, normalize, kl_factor, ctx_factor, state_factor)
         for idx, x in jobs:
+            if idx % CHUNK == 0:
+                tr.prefetch([j[1] for j in jobs[idx:idx + CHUNK]])
             trans[idx], pos[idx] = tr(x)
             if numpy.mod(idx, 10) == 0:
                 print('Sample ', (idx + 1), '/', n_samples, ' Done')
@@ -97,8 +109,8 @@ def main(model, dictionary, source_file, saveto, k=5, normalize=False, n_process
                                                            ctx_factor, state_factor)) for midx in range(n_process)]
         for p in procs:
             p.start()
-        for job in jobs:
-            queue.put(job)
+        for lo in range(0, len(jobs), CHUNK):
+            queue.put(jobs[lo:lo + CHUNK])
         for idx in range(n_samples):
             resp = rqueue.get()
             trans[resp[0]], pos[resp[0]] = resp[1], resp[2]

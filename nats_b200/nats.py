@@ -903,12 +903,71 @@ def build_sampler(tparams, options, trng=None):
         init_state = torch.empty((n, D), dtype=torch.float32, device=eng.device)
         ctx = torch.empty((Tx, n, C), dtype=torch.float32, device=eng.device)
         pctx = torch.empty((Tx, n, A), dtype=torch.float32, device=eng.device)
-        _lib.check(eng.lib.nats_sampler_init(eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(xd),
+        _lib.check(eng.lib.nats_sampler_init(eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(xd), None,
                                              Tx, n, _ptr(ws), nbytes, _ptr(init_state), _ptr(ctx), _ptr(pctx)),
                    'nats_sampler_init')
         eng.launches += 1
         host = ctx.cpu().numpy()
         return [init_state.cpu().numpy(), DeviceBackedArray(host, _CtxHandle(ctx, pctx, host))]
+
+    # ---- device-side f_init for the device-resident beam search: no host copies, and SEVERAL sentences per encoder launch.
+    # The persistent encoder kernel costs the same ~7 us per source position for 1 or 32 sentences, and at summary lengths
+    # f_init is more than half of a sentence's time: gen.py hands the next sentences to prefetch(), which encodes them in one
+    # masked launch (the training encoder's masks, nats.py:700-724) and parks the per-sentence slices.
+    cache = {}
+
+    def _key(x):
+        return numpy.ascontiguousarray(x, dtype='int64').reshape(-1).tobytes()
+
+    def prefetch(xs, max_batch=32):
+        """xs: iterable of source sentences ([Tx_i] or [Tx_i, 1] word ids, EOS included); encodes those not parked yet"""
+        todo = []
+        for x in xs:
+            k_ = _key(x)
+            if k_ not in cache and all(k_ != t[0] for t in todo):
+                todo.append((k_, numpy.ascontiguousarray(x, dtype='int64').reshape(-1)))
+        for lo in range(0, len(todo), max_batch):
+            grp = todo[lo:lo + max_batch]
+            n = len(grp)
+            Tx = max(len(v) for _, v in grp)
+            xb = numpy.zeros((Tx, n), dtype='int64')
+            mb = numpy.zeros((Tx, n), dtype='float32')
+            for i, (_, v) in enumerate(grp):
+                xb[:len(v), i] = v
+                mb[:len(v), i] = 1.
+            xd, md = torch.from_numpy(xb).to(eng.device), torch.from_numpy(mb).to(eng.device)
+            ws, nbytes = ws_for(Tx, n)
+            f32 = dict(dtype=torch.float32, device=eng.device)
+            init_state, ctx, pctx = torch.empty((n, D), **f32), torch.empty((Tx, n, C), **f32), torch.empty((Tx, n, A), **f32)
+            _lib.check(eng.lib.nats_sampler_init(eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(xd), _ptr(md),
+                                                 Tx, n, _ptr(ws), nbytes, _ptr(init_state), _ptr(ctx), _ptr(pctx)),
+                       'nats_sampler_init')
+            eng.launches += 1
+            for i, (k_, v) in enumerate(grp):
+                L = len(v)
+                cache[k_] = (init_state[i].clone(), ctx[:L, i].contiguous(), pctx[:L, i].contiguous())
+        while len(cache) > 4 * max_batch:                     # sentences that were never asked for
+            cache.pop(next(iter(cache)))
+
+    def init_device(x):
+        """-> (init_state [D], ctx [Tx, C], pctx [Tx, A]) device tensors of ONE sentence; parked results are used once"""
+        hit = cache.pop(_key(x), None)
+        if hit is not None:
+            return hit
+        x = numpy.ascontiguousarray(x, dtype='int64').reshape(-1, 1)
+        Tx = x.shape[0]
+        xd = torch.from_numpy(x).to(eng.device)
+        ws, nbytes = ws_for(Tx, 1)
+        f32 = dict(dtype=torch.float32, device=eng.device)
+        init_state, ctx, pctx = torch.empty((1, D), **f32), torch.empty((Tx, 1, C), **f32), torch.empty((Tx, 1, A), **f32)
+        _lib.check(eng.lib.nats_sampler_init(eng.ctx, eng.stream(), ctypes.byref(dims), _ptr(tparams.flat), _ptr(xd), None,
+                                             Tx, 1, _ptr(ws), nbytes, _ptr(init_state), _ptr(ctx), _ptr(pctx)),
+                   'nats_sampler_init')
+        eng.launches += 1
+        return init_state.reshape(D), ctx.reshape(Tx, C), pctx.reshape(Tx, A)
+
+    f_init.prefetch = prefetch
+    f_init.device = init_device
 
     def f_next(y, ctx, init_state, acc_ctx, acc_alpha):
         y = numpy.ascontiguousarray(y, dtype='int64')
@@ -1067,10 +1126,11 @@ def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_fac
     lib = eng.lib
     V, W, D, A = f_next.dims
     C = 2 * D
-    init_state, ctx0 = f_init(x)
-    handle = getattr(ctx0, '_nats_handle', None)
-    ctx_d, pctx_d = handle.ctx_dev, handle.pctx_dev
-    Tx = int(ctx0.shape[0])
+    x = numpy.asarray(x)
+    if x.ndim == 2 and x.shape[1] != 1:
+        raise ValueError('gen_sample decodes one source sentence at a time (x is [Tx, 1])')
+    init_state, ctx_d, pctx_d = f_init.device(x)                 # device tensors; parked by f_init.prefetch if it ran
+    Tx = int(ctx_d.shape[0])
     dev = eng.device
     f32 = dict(dtype=torch.float32, device=dev)
     i32 = dict(dtype=torch.int32, device=dev)
@@ -1079,7 +1139,7 @@ def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_fac
     state = [torch.zeros((k, D), **f32) for _ in range(2)]
     acc_ctx = [torch.zeros((k, C), **f32) for _ in range(2)]
     acc_alpha = [torch.zeros((k, Tx), **f32) for _ in range(2)]
-    state[0][0].copy_(torch.from_numpy(numpy.ascontiguousarray(init_state, dtype='float32')).reshape(-1)[:D])
+    state[0][0].copy_(init_state.reshape(-1)[:D])
     outs = [torch.empty((k, V), **f32), None, torch.empty((k, D), **f32),
             torch.empty((k, Tx), **f32), torch.empty((k, C), **f32), torch.empty((k, C), **f32), torch.empty((k, Tx), **f32)]
     hist_alpha = [torch.zeros((k, maxlen, Tx), **f32) for _ in range(2)]
@@ -1202,7 +1262,7 @@ def gen_sample(tparams, f_init, f_next, x, options, trng=None, k=1, maxlen=30, s
         assert not stochastic, 'Beam search does not support stochastic sampling'
     if (not stochastic and _scorer_factory is None and getattr(f_next, 'next_device', None) is not None and k <= 32
             and os.environ.get('NATS_DEVICE_BEAM', '1') != '0' and numpy.ndim(x) == 2 and numpy.shape(x)[1] == 1
-            and getattr(f_init, '__module__', None) == __name__):
+            and getattr(f_init, '__module__', None) == __name__ and hasattr(f_init, 'device')):
         return _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_factor, state_factor, _trace)
 
     sample, sample_score, sample_dec_alphas = [], [], []

@@ -149,6 +149,23 @@ def test_config5_softmax_cluster_matches_row_kernel(N, params):
     np.testing.assert_allclose(res[0], res[1], rtol=2e-6, atol=1e-12)
 
 
+def test_config5_batched_f_init_vs_oracle(N, params):
+    """Three sources of 400 / 250 / 31 words encoded in one masked launch of the persistent encoder kernel: init_state and
+    the valid rows of ctx equal the float64 oracle's single-sentence f_init."""
+    P = O.cast_params(params, 'float64')
+    rs = np.random.RandomState(21)
+    xs = [np.concatenate([rs.randint(2, 30000, size=L), [0]]).astype('int64') for L in (400, 250, 31)]
+    tparams = N.init_tparams(params)
+    f_init, f_next = N.build_sampler(tparams, OPTS)
+    f_init.prefetch(xs)
+    for x in xs:
+        s0, ctx, pctx = f_init.device(x)
+        r0, rctx = O.f_init(P, x[:, None])
+        np.testing.assert_allclose(s0.cpu().numpy(), r0[0], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(ctx.cpu().numpy(), rctx[:, 0], rtol=1e-4, atol=2e-6)
+        assert tuple(pctx.shape) == (len(x), 100)
+
+
 def test_config5_beam_vs_oracle(N, params):
     """10 beam steps, k = 10, all three distraction factors on, src_len 400: identical tokens, scores and penalty
     vectors (nats.py:981-999) as the literal restatement driven by the float64 oracle's f_init / f_next."""

@@ -305,6 +305,35 @@ def test_beam_search_wide_beams(N, k, model):
     assert all(len(a) == len(s) for a, s in zip(got_al, got_s))
 
 
+def test_f_init_prefetch_encodes_several_sentences_at_once(N):
+    """f_init.prefetch: ragged sentences in ONE masked encoder launch (nats_sampler_init with x_mask) give every sentence
+    the init_state / ctx / pctx of its own f_init (nats.py:789-817), and the beam search that consumes the parked result
+    returns what it returns without prefetch."""
+    opts = toy_options(D=32, W=8, A=12, V=120)
+    P32 = O.cast_params(toy_params(opts), 'float32')
+    tparams = N.init_tparams(P32)
+    rs = np.random.RandomState(17)
+    xs = [np.concatenate([rs.randint(2, 120, size=L), [0]]).astype('int64') for L in (5, 9, 3, 9, 14, 1)]
+    f_init, f_next = N.build_sampler(tparams, opts)
+    single = [tuple(t.clone() for t in f_init.device(x)) for x in xs]
+    f_init.prefetch(xs, max_batch=4)                       # two launches: 4 + 2 sentences
+    for x, ref in zip(xs, single):
+        got = f_init.device(x)
+        assert got[1].shape == ref[1].shape == (len(x), 64) and got[2].shape == (len(x), 12)
+        for g, r in zip(got, ref):
+            np.testing.assert_allclose(g.cpu().numpy(), r.cpu().numpy(), rtol=2e-4, atol=2e-6)
+        r0, rc = O.f_init(P32, x[:, None])
+        np.testing.assert_allclose(got[0].cpu().numpy(), r0[0], rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(got[1].cpu().numpy(), rc[:, 0], rtol=2e-4, atol=2e-6)
+    kw = dict(k=5, maxlen=7, stochastic=False, use_unk=True, kl_factor=0.5, ctx_factor=0.5, state_factor=0.5)
+    plain = [N.gen_sample(tparams, f_init, f_next, x[:, None], opts, **kw) for x in xs]
+    f_init.prefetch(xs)
+    for x, (ps, psc, _) in zip(xs, plain):
+        gs, gsc, _ = N.gen_sample(tparams, f_init, f_next, x[:, None], opts, **kw)
+        assert [list(map(int, s)) for s in gs] == [list(map(int, s)) for s in ps]
+        np.testing.assert_allclose(np.array(gsc, 'float64'), np.array(psc, 'float64'), rtol=2e-4)
+
+
 def test_beam_topk_matches_numpy(N):
     """nats_beam_topk: per row the k largest probabilities, descending, ties by ascending index, entry 1 -> 1e-20
     when use_unk is off (nats.py:975) -- the selection that replaces the host argsort of nats.py:997-999."""
