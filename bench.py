@@ -429,13 +429,13 @@ def beam_run(nats, tparams, opts, w, steps, warm=True, kernels=False):
     return out
 
 
-def gen_throughput(nats, tparams, opts, w, n_sent=16, steps=25):
+def gen_throughput(nats, tparams, opts, w, n_sent=32, steps=25):
     """What gen.py does per worker: a stream of source sentences, beam 10 each.  With f_init.prefetch the 16 encoders run
     as ONE masked launch of the persistent kernel; without, one launch per sentence.  EOS is suppressed: every sentence
     runs all `steps` steps (a summary-sized output)."""
     import torch
     rng = np.random.RandomState(99)
-    xs = [np.array(rng.randint(2, w['n_words'], size=(w['Tx'] - 1 - 7 * i,)).tolist() + [0], dtype='int64') for i in range(n_sent)]
+    xs = [np.array(rng.randint(2, w['n_words'], size=(w['Tx'] - 1 - 7 * (i % 16),)).tolist() + [0], dtype='int64') for i in range(n_sent)]
     f_init, f_next = nats.build_sampler(tparams, opts, None)
     bsave = tparams['ff_logit_b'].get_value()
     bmod = bsave.copy()
@@ -443,14 +443,17 @@ def gen_throughput(nats, tparams, opts, w, n_sent=16, steps=25):
     tparams['ff_logit_b'].set_value(bmod)
     out = {}
     try:
-        for mode in ('one_f_init_per_sentence', 'prefetch_16'):
+        for mode in ('one_f_init_per_sentence', 'prefetch_16', 'prefetch_16_and_8_searches_in_flight'):
             for rep in range(2):                              # first pass warms buffers and kernels
                 torch.cuda.synchronize()
                 t0 = time.time()
-                if mode == 'prefetch_16':
-                    f_init.prefetch(xs)
-                for x in xs:
-                    nats.gen_sample(tparams, f_init, f_next, x[:, None], opts, None, 10, steps, False, False, True, 1.0, 1.0, 1.0)
+                if mode == 'prefetch_16_and_8_searches_in_flight':
+                    nats.gen_sample_many(tparams, f_init, f_next, xs, opts, None, 10, steps, True, 1.0, 1.0, 1.0, concurrency=8, chunk=16)
+                else:
+                    for i, x in enumerate(xs):
+                        if mode == 'prefetch_16' and i % 16 == 0:
+                            f_init.prefetch(xs[i:i + 16])
+                        nats.gen_sample(tparams, f_init, f_next, x[:, None], opts, None, 10, steps, False, False, True, 1.0, 1.0, 1.0)
                 torch.cuda.synchronize()
                 dt = time.time() - t0
             out[mode] = {'sentences_per_s': n_sent / dt, 'ms_per_sentence': dt / n_sent * 1e3,
@@ -458,7 +461,7 @@ def gen_throughput(nats, tparams, opts, w, n_sent=16, steps=25):
     finally:
         tparams['ff_logit_b'].set_value(bsave)
     out['how'] = '%d sentences of src_len %d..%d, beam 10, %d steps each, kl=ctx=state=1; wall clock incl. f_init and result copies' % (
-        n_sent, w['Tx'] - 1 - 7 * (n_sent - 1), w['Tx'] - 1, steps)
+        n_sent, w['Tx'] - 1 - 7 * 15, w['Tx'] - 1, steps)
     return out
 
 

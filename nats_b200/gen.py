@@ -43,12 +43,24 @@ class _Translator(object):
         if pf is not None and self.k <= 32 and os.environ.get('NATS_DEVICE_BEAM', '1') != '0':
             pf([numpy.array(s, dtype='int64') for s in seqs])
 
+    def many(self, seqs):
+        """a chunk of sentences: encoders in one launch, several beam searches in flight (nats.gen_sample_many)"""
+        kl, cf, sf = self.factors
+        outs = self.nats.gen_sample_many(self.tparams, self.f_init, self.f_next, [numpy.array(s, dtype='int64') for s in seqs],
+                                         self.options, trng=None, k=self.k, maxlen=100, use_unk=True, kl_factor=kl,
+                                         ctx_factor=cf, state_factor=sf, concurrency=int(os.environ.get('NATS_GEN_STREAMS', '8')),
+                                         chunk=CHUNK)
+        return [self._best(*o) for o in outs]
+
     def __call__(self, seq):
         kl, cf, sf = self.factors
         sample, score, alphas = self.nats.gen_sample(
             self.tparams, self.f_init, self.f_next, numpy.array(seq, dtype='int64').reshape([len(seq), 1]), self.options,
             trng=None, k=self.k, maxlen=100, stochastic=False, argmax=False, use_unk=True, kl_factor=kl, ctx_factor=cf,
             state_factor=sf)
+        return self._best(sample, score, alphas)
+
+    def _best(self, sample, score, alphas):
         score = numpy.array(score, dtype='float64')
         if self.normalize:
             score = score / numpy.array([len(s) for s in sample])
@@ -67,10 +79,8 @@ def translate_model(queue, rqueue, pid, model, options, k, normalize, kl_factor,
         req = queue.get()
         if req is None:
             break
-        tr.prefetch([x for _, x in req])                       # a chunk of jobs: one encoder launch for all of them
-        for idx, x in req:
-            print(pid, '-', idx)
-            seq, pos = tr(x)
+        print(pid, '-', req[0][0], '..', req[-1][0])            # a chunk of jobs
+        for (idx, _), (seq, pos) in zip(req, tr.many([x for _, x in req])):
             rqueue.put((idx, seq, pos))
 
 
@@ -96,12 +106,10 @@ def main(model, dictionary, source_file, saveto, k=5, normalize=False, n_process
     trans, pos = [None] * n_samples, [None] * n_samples
     if n_process <= 1:
         tr = _Translator(model, options, k, normalize, kl_factor, ctx_factor, state_factor)
-        for idx, x in jobs:
-            if idx % CHUNK == 0:
-                tr.prefetch([j[1] for j in jobs[idx:idx + CHUNK]])
-            trans[idx], pos[idx] = tr(x)
-            if numpy.mod(idx, 10) == 0:
-                print('Sample ', (idx + 1), '/', n_samples, ' Done')
+        for lo in range(0, len(jobs), CHUNK):
+            for (idx, _), (seq, p_) in zip(jobs[lo:lo + CHUNK], tr.many([j[1] for j in jobs[lo:lo + CHUNK]])):
+                trans[idx], pos[idx] = seq, p_
+            print('Sample ', min(lo + CHUNK, n_samples), '/', n_samples, ' Done')
     else:
         ctx = mp.get_context('spawn')                          # CUDA contexts do not survive fork
         queue, rqueue = ctx.Queue(), ctx.Queue()

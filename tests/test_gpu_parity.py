@@ -334,6 +334,27 @@ def test_f_init_prefetch_encodes_several_sentences_at_once(N):
         np.testing.assert_allclose(np.array(gsc, 'float64'), np.array(psc, 'float64'), rtol=2e-4)
 
 
+@pytest.mark.parametrize('concurrency', [1, 3])
+def test_gen_sample_many_equals_sentence_by_sentence(N, concurrency):
+    """gen_sample_many: searches interleaved on separate CUDA streams (own workspace each), encoders batched -- every
+    sentence gets exactly the hypotheses, scores and attention histories of its own gen_sample call (nats.py:879-1076)."""
+    opts = toy_options(D=32, W=8, A=12, V=120)
+    P32 = O.cast_params(toy_params(opts), 'float32')
+    tparams = N.init_tparams(P32)
+    rs = np.random.RandomState(23)
+    xs = [np.concatenate([rs.randint(2, 120, size=L), [0]]).astype('int64') for L in (6, 11, 3, 11, 17, 2, 9, 9)]
+    f_init, f_next = N.build_sampler(tparams, opts)
+    kw = dict(k=6, maxlen=9, use_unk=True, kl_factor=0.5, ctx_factor=0.5, state_factor=0.5)
+    one = [N.gen_sample(tparams, f_init, f_next, x[:, None], opts, stochastic=False, **kw) for x in xs]
+    many = N.gen_sample_many(tparams, f_init, f_next, xs, opts, concurrency=concurrency, chunk=5, **kw)
+    assert len(many) == len(xs)
+    for (s1, c1, a1), (s2, c2, a2) in zip(one, many):
+        assert [list(map(int, s)) for s in s2] == [list(map(int, s)) for s in s1]
+        np.testing.assert_allclose(np.array(c2, 'float64'), np.array(c1, 'float64'), rtol=2e-4)
+        for h1, h2 in zip(a1, a2):
+            np.testing.assert_allclose(np.array(h2), np.array(h1), rtol=2e-4, atol=1e-6)
+
+
 def test_beam_topk_matches_numpy(N):
     """nats_beam_topk: per row the k largest probabilities, descending, ties by ascending index, entry 1 -> 1e-20
     when use_unk is off (nats.py:975) -- the selection that replaces the host argsort of nats.py:997-999."""
