@@ -443,12 +443,12 @@ def gen_throughput(nats, tparams, opts, w, n_sent=32, steps=25):
     tparams['ff_logit_b'].set_value(bmod)
     out = {}
     try:
-        for mode in ('one_f_init_per_sentence', 'prefetch_16', 'prefetch_16_and_8_searches_in_flight'):
+        for mode in ('one_f_init_per_sentence', 'prefetch_16', 'prefetch_16_and_12_searches_in_flight'):
             for rep in range(2):                              # first pass warms buffers and kernels
                 torch.cuda.synchronize()
                 t0 = time.time()
-                if mode == 'prefetch_16_and_8_searches_in_flight':
-                    nats.gen_sample_many(tparams, f_init, f_next, xs, opts, None, 10, steps, True, 1.0, 1.0, 1.0, concurrency=8, chunk=16)
+                if mode == 'prefetch_16_and_12_searches_in_flight':
+                    nats.gen_sample_many(tparams, f_init, f_next, xs, opts, None, 10, steps, True, 1.0, 1.0, 1.0, concurrency=12, chunk=16)
                 else:
                     for i, x in enumerate(xs):
                         if mode == 'prefetch_16' and i % 16 == 0:

@@ -48,7 +48,7 @@ class _Translator(object):
         kl, cf, sf = self.factors
         outs = self.nats.gen_sample_many(self.tparams, self.f_init, self.f_next, [numpy.array(s, dtype='int64') for s in seqs],
                                          self.options, trng=None, k=self.k, maxlen=100, use_unk=True, kl_factor=kl,
-                                         ctx_factor=cf, state_factor=sf, concurrency=int(os.environ.get('NATS_GEN_STREAMS', '8')),
+                                         ctx_factor=cf, state_factor=sf, concurrency=int(os.environ.get('NATS_GEN_STREAMS', '12')),
                                          chunk=CHUNK)
         return [self._best(*o) for o in outs]
 

@@ -1161,7 +1161,10 @@ class _DeviceBeam(object):
         hist_ctx = [torch.zeros((k, maxlen, C), **f32) for _ in range(2)] if distract else [None, None]
         hist_state = [torch.zeros((k, maxlen, D), **f32) for _ in range(2)] if distract else [None, None]
         out_alpha = torch.zeros((k, maxlen, Tx), **f32)
-        counters = torch.tensor([1, 0, 0, 0, -1, 0, 0, 0], **i32)          # live_k, dead_k, done, finished, last effective step
+        c0 = getattr(eng, '_beam_counters0', None)               # live_k, dead_k, done, finished, last effective step
+        if c0 is None:                                           # (a host list -> device tensor is a synchronous copy: once)
+            c0 = eng._beam_counters0 = torch.tensor([1, 0, 0, 0, -1, 0, 0, 0], **i32)
+        counters = c0.clone()
         scores = torch.zeros((2, k), **f32)
         tokens = torch.zeros((2, k, maxlen), **i32)
         parents = torch.zeros((k,), **i32)
@@ -1282,7 +1285,7 @@ class _DeviceBeam(object):
             L = int(fin_len[f])
             sample.append([int(t) for t in fin_tok[f, :L]])
             sample_score.append(numpy.float32(fin_sc[f]))
-            sample_dec_alphas.append([fin_al[f, t].copy() for t in range(L)])
+            sample_dec_alphas.append(list(fin_al[f, :L].copy()))       # one copy; the rows are views of it
         if live_k > 0:                                            # dump what is still alive (nats.py:1068-1074)
             s_last = int(cnt[4])                                  # step s wrote the rows of parity (s + 1) & 1, s + 1 words each
             par, L = (s_last + 1) & 1, s_last + 1
@@ -1290,7 +1293,7 @@ class _DeviceBeam(object):
             for j in range(live_k):
                 sample.append([int(t) for t in lt[j, :L]])
                 sample_score.append(numpy.float32(ls[j]))
-                sample_dec_alphas.append([ha[j, t].copy() for t in range(L)])
+                sample_dec_alphas.append(list(ha[j, :L].copy()))
         return sample, sample_score, sample_dec_alphas
 
 
@@ -1303,11 +1306,11 @@ def _gen_sample_device(f_init, f_next, x, k, maxlen, use_unk, kl_factor, ctx_fac
 
 
 def gen_sample_many(tparams, f_init, f_next, xs, options, trng=None, k=5, maxlen=30, use_unk=False, kl_factor=0,
-                    ctx_factor=0, state_factor=0, concurrency=8, chunk=16):
+                    ctx_factor=0, state_factor=0, concurrency=12, chunk=16):
     """Beam search (nats.py:879-1076, stochastic=False) of a LIST of source sentences -> list of gen_sample's three lists.
     A beam step is a chain of ~18 small dependent kernels that leaves most of the GPU idle and costs the host ~40 us to
     issue against ~180 us of device time, so `concurrency` searches run interleaved, each on its own CUDA stream with its
-    own workspace (measured: 196 / 250 / 307 / 349 / 350 sentences/s with 1 / 2 / 4 / 8 / 12 in flight); the encoders of every `chunk` sentences run as one masked launch (f_init.prefetch).  Results are those
+    own workspace (measured: 210 / 281 / 332 / 375 / 407 sentences/s with 1 / 2 / 4 / 8 / 12 in flight); the encoders of every `chunk` sentences run as one masked launch (f_init.prefetch).  Results are those
     of gen_sample sentence by sentence (the searches do not interact)."""
     eng = f_next.engine
     torch = eng.torch
@@ -1322,21 +1325,32 @@ def gen_sample_many(tparams, f_init, f_next, xs, options, trng=None, k=5, maxlen
     main = torch.cuda.current_stream(eng.device)
     results = [None] * len(xs)
     nxt, parked_upto, active = 0, 0, {}
-    while nxt < len(xs) or active:
-        for slot in range(concurrency):
-            if slot not in active and nxt < len(xs):
-                if nxt >= parked_upto:
-                    f_init.prefetch(xs[nxt:nxt + chunk])          # on the current stream
-                    parked_upto = nxt + chunk
-                streams[slot].wait_stream(main)                   # the encoder launch precedes the search that reads it
-                active[slot] = (nxt, _DeviceBeam(f_init, f_next, numpy.asarray(xs[nxt]).reshape(-1, 1), k, maxlen, use_unk,
-                                                 kl_factor, ctx_factor, state_factor, None, slot + 1, streams[slot]))
-                nxt += 1
+
+    def start(slot):
+        nonlocal nxt, parked_upto
+        if nxt >= parked_upto:
+            f_init.prefetch(xs[nxt:nxt + chunk])                  # on the current stream
+            parked_upto = nxt + chunk
+        streams[slot].wait_stream(main)                           # the encoder launch precedes the search that reads it
+        b = _DeviceBeam(f_init, f_next, numpy.asarray(xs[nxt]).reshape(-1, 1), k, maxlen, use_unk, kl_factor, ctx_factor,
+                        state_factor, None, slot + 1, streams[slot])
+        active[slot] = (nxt, b)
+        nxt += 1
+        b.step()
+
+    for slot in range(min(concurrency, len(xs))):
+        start(slot)
+    while active:
+        finished = []
         for slot in list(active):
             idx, b = active[slot]
             if not b.step():
-                results[idx] = b.result()
+                finished.append((idx, b))
                 del active[slot]
+                if nxt < len(xs):
+                    start(slot)              # queued behind the finished search on the same stream (same workspace slot)
+        for idx, b in finished:              # fetching a result waits for that search only; the others have work queued
+            results[idx] = b.result()
     return results
 
 
