@@ -33,9 +33,7 @@ int train_readout_bwd(const nats_ctx* ctx, cudaStream_t st, const nats_dims_t& d
     NATS_TRY(ga(ctx, st, w, gemm_problem(w.d_h2, D, w.dpre, W, G + o.lstm_W, W, D, W, YB), true, false));
     NATS_TRY(ga(ctx, st, w, gemm_problem(w.embs, W, w.dpre, W, G + o.prev_W, W, W, W, YB), true, false));
     NATS_TRY(ga(ctx, st, w, gemm_problem(w.d_ctx, C, w.dpre, W, G + o.ctxr_W, W, C, W, YB), true, false));
-    NATS_TRY(colsum(st, w.dpre, YB, W, W, G + o.lstm_b, 0, w.red_scratch));
-    NATS_TRY(colsum(st, w.dpre, YB, W, W, G + o.prev_b, 0, w.red_scratch));
-    NATS_TRY(colsum(st, w.dpre, YB, W, W, G + o.ctxr_b, 0, w.red_scratch));
+    NATS_TRY(colsum3(st, w.dpre, YB, W, W, G + o.lstm_b, G + o.prev_b, G + o.ctxr_b, 0, w.red_scratch));   // one sum, three biases
     NATS_TRY(ga(ctx, st, w, gemm_problem(w.dpre, W, params + o.lstm_W, W, w.dh2_ro, D, YB, D, W), false, true));
     NATS_TRY(ga(ctx, st, w, gemm_problem(w.dpre, W, params + o.ctxr_W, W, w.dctx_ro, C, YB, C, W), false, true));
     NATS_TRY(ga(ctx, st, w, gemm_problem(w.dpre, W, params + o.prev_W, W, w.dembs, W, YB, W, W), false, true));

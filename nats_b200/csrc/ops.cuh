@@ -109,6 +109,9 @@ int mask_lengths(cudaStream_t st, const float* mask, int Tx, int B, float* xlen,
 int scale_rows(cudaStream_t st, const float* src, const float* inv, int B, int C, float* out);
 // out[n] (+)= sum_k X[k*ld + n]                  (bias gradients)
 int colsum(cudaStream_t st, const float* X, long long K, int N, int ld, float* out, int accumulate, float* scratch);
+// the same column sums written to three outputs
+int colsum3(cudaStream_t st, const float* X, long long K, int N, int ld, float* out, float* out2, float* out3, int accumulate,
+            float* scratch);
 // out[n] (+)= sum_k X[k*ld+n] * Y[k*ld+n]        (d U_con, d W_con)
 int colsum_prod(cudaStream_t st, const float* X, const float* Y, long long K, int N, int ld, float* out,
                 int accumulate, float* scratch);

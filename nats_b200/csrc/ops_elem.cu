@@ -179,12 +179,15 @@ __global__ void colsum_stage1(const float* __restrict__ X, const float* __restri
         part[(long long)blockIdx.y * N + n] = t;
     }
 }
-__global__ void colsum_stage2(const float* __restrict__ part, int ks, int N, float* __restrict__ out, int accumulate) {
+__global__ void colsum_stage2(const float* __restrict__ part, int ks, int N, float* __restrict__ out, int accumulate,
+                              float* __restrict__ out2, float* __restrict__ out3) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float s = 0.f;
     for (int i = 0; i < ks; ++i) s += part[(long long)i * N + n];
     out[n] = accumulate ? out[n] + s : s;
+    if (out2) out2[n] = accumulate ? out2[n] + s : s;       // the same sums feed several gradients (three readout biases)
+    if (out3) out3[n] = accumulate ? out3[n] + s : s;
 }
 
 __global__ void cost_reduce_kernel(const float* __restrict__ rowcost, int Ty, int B, float* __restrict__ cost,
@@ -288,7 +291,7 @@ int scale_rows(cudaStream_t st, const float* src, const float* inv, int B, int C
 }
 
 static int colsum_impl(cudaStream_t st, const float* X, const float* Y, long long K, int N, int ld, float* out,
-                       int accumulate, float* scratch) {
+                       int accumulate, float* scratch, float* out2 = nullptr, float* out3 = nullptr) {
     if (N == 0) return 0;
     int ks = (int)((K + 255) / 256);
     if (ks > 64) ks = 64;
@@ -299,12 +302,16 @@ static int colsum_impl(cudaStream_t st, const float* X, const float* Y, long lon
     if (Y) colsum_stage1<true><<<grid, block, 0, st>>>(X, Y, K, N, ld, rows_per, scratch);
     else colsum_stage1<false><<<grid, block, 0, st>>>(X, nullptr, K, N, ld, rows_per, scratch);
     NATS_LAUNCH_OK();
-    colsum_stage2<<<cdiv(N, 256), 256, 0, st>>>(scratch, ks, N, out, accumulate);
+    colsum_stage2<<<cdiv(N, 256), 256, 0, st>>>(scratch, ks, N, out, accumulate, out2, out3);
     NATS_LAUNCH_OK();
     return 0;
 }
 int colsum(cudaStream_t st, const float* X, long long K, int N, int ld, float* out, int accumulate, float* scratch) {
     return colsum_impl(st, X, nullptr, K, N, ld, out, accumulate, scratch);
+}
+int colsum3(cudaStream_t st, const float* X, long long K, int N, int ld, float* out, float* out2, float* out3, int accumulate,
+            float* scratch) {
+    return colsum_impl(st, X, nullptr, K, N, ld, out, accumulate, scratch, out2, out3);
 }
 int colsum_prod(cudaStream_t st, const float* X, const float* Y, long long K, int N, int ld, float* out,
                 int accumulate, float* scratch) {
