@@ -105,3 +105,15 @@ def test_py3_drivers(tmp_path):
         assert len(toks) % 2 == 0
         for w, p in zip(toks[0::2], toks[1::2]):
             assert (w in worddict or w == 'UNK') and p.startswith('[') and 0 <= int(p[1:-1]) < ns
+    # -p 2: two spawned worker processes (model replicas) fed with chunks of sentences -- same file, line for line
+    out2 = str(tmp_path / 'gen_p2.txt')
+    gen.main(model, dic, va[0], out2, k=3, normalize=True, n_process=2, kl_factor=0.5, ctx_factor=0.5, state_factor=0.5)
+    assert open(out2).read() == open(out).read()
+    # one search at a time on the current stream (NATS_GEN_STREAMS=1) gives the same file as 12 in flight
+    os.environ['NATS_GEN_STREAMS'] = '1'
+    try:
+        out3 = str(tmp_path / 'gen_s1.txt')
+        gen.main(model, dic, va[0], out3, k=3, normalize=True, n_process=1, kl_factor=0.5, ctx_factor=0.5, state_factor=0.5)
+    finally:
+        del os.environ['NATS_GEN_STREAMS']
+    assert open(out3).read() == open(out).read()
