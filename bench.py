@@ -690,6 +690,7 @@ def main():
     if world == 1 and args.workload == 'c3' and not args.no_regions:
         try:
             r3 = beam_run(nats, tparams, opts, WORKLOADS['c5'], 20)
+            r3['gen_stream'] = gen_throughput(nats, tparams, opts, WORKLOADS['c5'])      # sentences/s of the gen driver's loop
         except Exception as e:
             r3 = {'error': repr(e)}
 
