@@ -1222,6 +1222,8 @@ class _DeviceBeam(object):
             a.hist_ctx_out = hist_ctx[c ^ 1].data_ptr() if distract else None
             a.hist_state_out = hist_state[c ^ 1].data_ptr() if distract else None
             one_call.append((eng.ctx, stream, ctypes.byref(dims_), ctypes.byref(a)))
+        # every local becomes an attribute: step() / result() use a dozen of them, and ALL the tensors above must outlive the
+        # search because their addresses sit in the prebuilt argument structs (a tensor dropped here would be a dangling pointer)
         keep = dict(locals())
         keep.pop('self')
         self.__dict__.update(keep)
